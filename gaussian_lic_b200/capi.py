@@ -1,0 +1,81 @@
+"""ctypes bindings of the C ABI (include/glic_b200.h) -- plumbing only.
+
+Device memory comes from torch tensors (`tensor.data_ptr()`); every byte of compute happens in
+libglic_b200.so.  There is no fallback: if the library is missing, import fails loudly.
+"""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libglic_b200.so")
+
+GLIC_OK = 0
+
+
+class GlicError(RuntimeError):
+    pass
+
+
+class View(C.Structure):
+    _fields_ = [("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("limx_neg", C.c_float), ("limx_pos", C.c_float), ("limy_neg", C.c_float), ("limy_pos", C.c_float),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "gaussian_lic_b200: %s is missing. Build it with `python gaussian_lic_b200/build.py` "
+            "(or __graft_entry__.build()); there is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i64, i32, f32, u32 = C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_float, C.c_uint32
+    sig = {
+        "glic_last_error": (C.c_char_p, []),
+        "glic_abi_version": (i32, []),
+        "glic_launch_count": (C.c_uint64, []),
+        "glic_geom_bytes": (sz, [i32]),
+        "glic_image_bytes": (sz, [i32, i32]),
+        "glic_binning_bytes": (sz, [i64]),
+        "glic_sample_bytes": (sz, [i64, i32, i32]),
+        "glic_max_buckets": (i64, [i64, i32, i32]),
+        "glic_sort_temp_bytes": (sz, [i64]),
+        "glic_loss_scratch_bytes": (sz, [i32, i32, i32]),
+        "glic_knn_temp_bytes": (sz, [i32]),
+        "glic_forward_preprocess": (i32, [i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, C.POINTER(View), i32, vp, vp, sz,
+                                          vp, sz, C.POINTER(i64), vp]),
+        "glic_forward_render": (i32, [i32, C.POINTER(View), i32, i64, vp, vp, vp, sz, vp, sz, vp, vp, C.POINTER(i64), vp]),
+        "glic_backward": (i32, [i32, i32, i32, vp, vp, f32, vp, vp, vp, C.POINTER(View), vp, i64, vp, vp, vp, vp, vp, f32,
+                                vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_sort_pairs_u64_u32": (i32, [i64, i32, vp, vp, vp, vp, vp, sz, vp]),
+        "glic_adam_update": (i32, [vp, vp, vp, vp, vp, f32, f32, f32, f32, u32, u32, vp]),
+        "glic_fused_ssim": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_fused_ssim_backward": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_l1_ssim_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
+        "glic_knn_mean_dist2": (i32, [i32, vp, vp, vp, sz, vp]),
+        "glic_debug_geom": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_debug_binning": (i32, [i64, vp, vp, vp, vp]),
+        "glic_debug_image": (i32, [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, SYMBOLS = _load()
+
+
+def check(status, what):
+    if status != GLIC_OK:
+        raise GlicError("glic_b200 %s failed (%d): %s" % (what, status, lib.glic_last_error().decode()))
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(lib.glic_launch_count())

@@ -1,0 +1,217 @@
+// common.cuh -- shared declarations of the glic_b200 CUDA library (sm_100a only).
+//
+// Workspace layouts (all opaque to callers; see DESIGN.md "HBM layout"):
+//   geom_ws   : GeomHeader | rec[3P] float4 (48 B AoS splat record) | offsets[P] u32 (inclusive
+//               scan of tiles_touched) | clamped[P] u8 | look-back status u64[blocks]
+//   image_ws  : ImageHeader | ranges[T] uint2 | bucket_offsets[T] u32 | max_contrib[T] u32 |
+//               n_contrib[HW] u32 | pixel_colors[3HW] f32
+//   binning_ws: BinHeader | keys[2][R] u64 | vals[2][R] u32 | sort temp
+//   sample_ws : bucket_to_tile[Bmax] u32 | ckpt[Bmax*256] float4 (T, C.r, C.g, C.b)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/glic_b200.h"
+
+namespace glic {
+
+constexpr int TILE = GLIC_TILE;
+constexpr int TILE_PIX = TILE * TILE;   // 256 pixels, one CTA
+constexpr int BUCKET = GLIC_BUCKET;     // 32 splats per checkpoint bucket
+constexpr int PRE_THREADS = 256;        // Gaussians per preprocess CTA
+
+// ---- error plumbing --------------------------------------------------------------------
+void set_error(const std::string& s);
+extern unsigned long long g_launches;
+
+#define GLIC_CUDA_TRY(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            glic::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+            return GLIC_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define GLIC_LAUNCH_CHECK()                                                                   \
+    do {                                                                                      \
+        ++glic::g_launches;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            glic::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));       \
+            return GLIC_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// ---- arena carving (128-byte aligned sub-arrays) ----------------------------------------
+struct Carver {
+    char* base;
+    size_t off;
+    __host__ explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+    template <typename T>
+    __host__ T* take(size_t count) {
+        off = (off + 127) & ~size_t(127);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+    __host__ size_t total() const { return (off + 127) & ~size_t(127); }
+};
+
+// Splat record, 48 bytes: three float4 per Gaussian (AoS so one gather = 1.5 sectors).
+//   r0 = (x, y, conic.x, conic.y)   r1 = (conic.z, opacity, red, green)
+//   r2 = (blue, depth, radius as int bits, tiles_touched as uint bits)
+struct GeomHeader {
+    unsigned int ticket;        // dynamic CTA id for the fused scan
+    unsigned int total;         // R = sum of tiles_touched
+    unsigned int visible;       // #Gaussians with radius > 0
+    unsigned int pad[29];
+};
+
+struct GeomState {
+    GeomHeader* hdr;
+    float4* rec;
+    uint32_t* offsets;
+    uint8_t* clamped;
+    unsigned long long* scan_status;
+    __host__ static GeomState carve(void* ws, int P, size_t* bytes = nullptr) {
+        Carver c(ws);
+        GeomState g;
+        g.hdr = c.take<GeomHeader>(1);
+        g.rec = c.take<float4>(size_t(3) * P);
+        g.offsets = c.take<uint32_t>(P);
+        g.clamped = c.take<uint8_t>(P);
+        g.scan_status = c.take<unsigned long long>((P + PRE_THREADS - 1) / PRE_THREADS + 1);
+        if (bytes) *bytes = c.total();
+        return g;
+    }
+};
+
+struct ImageHeader {
+    long long num_rendered;     // R
+    unsigned int num_buckets;   // B
+    unsigned int pad[29];
+};
+
+struct ImageState {
+    ImageHeader* hdr;
+    uint2* ranges;
+    uint32_t* bucket_offsets;
+    uint32_t* max_contrib;
+    uint32_t* n_contrib;
+    float* pixel_colors;
+    __host__ static ImageState carve(void* ws, int W, int H, size_t* bytes = nullptr) {
+        const size_t T = size_t((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        const size_t HW = size_t(W) * H;
+        Carver c(ws);
+        ImageState s;
+        s.hdr = c.take<ImageHeader>(1);
+        s.ranges = c.take<uint2>(T);
+        s.bucket_offsets = c.take<uint32_t>(T);
+        s.max_contrib = c.take<uint32_t>(T);
+        s.n_contrib = c.take<uint32_t>(HW);
+        s.pixel_colors = c.take<float>(3 * HW);
+        if (bytes) *bytes = c.total();
+        return s;
+    }
+};
+
+struct BinHeader {
+    unsigned int sorted_in_b;   // 1 when the sorted list lives in keys[1]/vals[1]
+    unsigned int pad[31];
+};
+
+size_t sort_temp_bytes(int64_t n);
+
+struct BinningState {
+    BinHeader* hdr;
+    uint64_t* keys[2];
+    uint32_t* vals[2];
+    void* sort_temp;
+    size_t sort_temp_size;
+    __host__ static BinningState carve(void* ws, int64_t R, size_t* bytes = nullptr) {
+        const size_t n = R > 0 ? size_t(R) : 1;
+        Carver c(ws);
+        BinningState b;
+        b.hdr = c.take<BinHeader>(1);
+        b.keys[0] = c.take<uint64_t>(n);
+        b.keys[1] = c.take<uint64_t>(n);
+        b.vals[0] = c.take<uint32_t>(n);
+        b.vals[1] = c.take<uint32_t>(n);
+        b.sort_temp_size = sort_temp_bytes(R);
+        b.sort_temp = c.take<char>(b.sort_temp_size);
+        if (bytes) *bytes = c.total();
+        return b;
+    }
+};
+
+struct SampleState {
+    uint32_t* bucket_to_tile;
+    float4* ckpt;               // [Bmax][256] (T, C.r, C.g, C.b) per pixel per bucket
+    __host__ static SampleState carve(void* ws, int64_t max_buckets, size_t* bytes = nullptr) {
+        const size_t n = max_buckets > 0 ? size_t(max_buckets) : 1;
+        Carver c(ws);
+        SampleState s;
+        s.bucket_to_tile = c.take<uint32_t>(n);
+        s.ckpt = c.take<float4>(n * TILE_PIX);
+        if (bytes) *bytes = c.total();
+        return s;
+    }
+};
+
+// getHigherMsb (rasterizer_impl.cu:42-57): number of tile-id bits included in the sort.
+inline uint32_t higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4, step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+// View parameters passed by value to kernels (pointers stay device pointers).
+struct ViewParams {
+    const float* view;
+    const float* proj;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    float limx_neg, limx_pos, limy_neg, limy_pos;
+    int W, H, grid_x, grid_y;
+};
+
+inline ViewParams make_view_params(const glic_view* v) {
+    ViewParams p;
+    p.view = v->viewmatrix; p.proj = v->projmatrix; p.campos = v->campos;
+    p.tan_fovx = v->tan_fovx; p.tan_fovy = v->tan_fovy;
+    p.focal_y = v->height / (2.0f * v->tan_fovy);     // rasterizer_impl.cu:348-349
+    p.focal_x = v->width / (2.0f * v->tan_fovx);
+    p.limx_neg = v->limx_neg; p.limx_pos = v->limx_pos; p.limy_neg = v->limy_neg; p.limy_pos = v->limy_pos;
+    p.W = v->width; p.H = v->height;
+    p.grid_x = (v->width + TILE - 1) / TILE; p.grid_y = (v->height + TILE - 1) / TILE;
+    return p;
+}
+
+// ---- stage launchers (defined in the .cu files) ------------------------------------------
+int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
+                              const float* rots, const float* opac, const float* dc, const float* sh,
+                              const ViewParams& vp, bool no_color, int* radii, GeomState g, cudaStream_t s);
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint64_t* keys, uint32_t* vals, cudaStream_t s);
+// Sorts on bits [0,end_bit); returns 0/1 = index of the ping-pong buffer holding the result, <0 on error.
+int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                      cudaStream_t s);
+int launch_tile_ranges(int64_t R, const uint64_t* keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s);
+int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* point_list, GeomState g, ImageState img,
+                          SampleState smp, float* out_color, float* out_final_T, cudaStream_t s);
+int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,
+                           ImageState img, SampleState smp, const float* dL_dpix, float* dL_dmean2D /*[P,3]*/,
+                           float* dL_dconic /*[P,4]*/, float* dL_dopacity, float* dL_dcolors, cudaStream_t s);
+int launch_preprocess_backward(int P, int D, int M, const float* means, const float* scales, float mod,
+                               const float* rots, const float* sh, const ViewParams& vp, const int* radii, GeomState g,
+                               float lambda_erank, const float* dL_dmean2D, const float* dL_dconic,
+                               const float* dL_dcolors, float* dL_dmeans3D, float* dL_dcov3D, float* dL_ddc,
+                               float* dL_dsh, float* dL_dscales, float* dL_drots, cudaStream_t s);
+
+}  // namespace glic

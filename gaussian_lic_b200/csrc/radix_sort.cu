@@ -1,0 +1,281 @@
+// radix_sort.cu -- CUB-free "onesweep" least-significant-digit radix sort of (u64 key, u32 value)
+// pairs on key bits [0, end_bit).  Stable.
+//
+// Replaces cub::DeviceRadixSort::SortPairs(begin_bit = 0, end_bit = 32 + bit) as called at
+// reference rasterizer_impl.cu:417-424 (and the Morton sort of simple_knn.cu:210-213).
+//
+// Structure (8-bit digits, ceil(end_bit/8) passes):
+//   1. one histogram kernel builds the global digit histogram of EVERY pass in a single read of
+//      the keys (8 B/pair);
+//   2. a tiny kernel turns each histogram into exclusive digit offsets;
+//   3. one kernel per pass: each CTA ranks a 4096-pair tile (warp-synchronous match-any ranking,
+//      stable), resolves its global digit offsets with a per-digit decoupled look-back chain over
+//      dynamically ordered CTAs (no second read of the data), stages the tile in shared memory in
+//      sorted order and writes digit runs out coalesced (24 B/pair/pass).
+// Algorithmic HBM traffic: (8 + 24*passes) B per pair (152 B @ 45 bits).
+#include "common.cuh"
+#include <algorithm>
+
+namespace glic {
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per CTA
+constexpr int MAX_PASSES = 8;
+
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
+
+struct SortTemp {
+    uint32_t* hist;     // [MAX_PASSES][RADIX]  digit histograms -> exclusive offsets
+    uint32_t* tickets;  // [MAX_PASSES]
+    uint32_t* status;   // [passes][blocks][RADIX]
+};
+
+__host__ inline int64_t sort_blocks(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+__host__ inline SortTemp carve_sort_temp(void* temp) {
+    char* p = static_cast<char*>(temp);
+    SortTemp t;
+    t.hist = reinterpret_cast<uint32_t*>(p);
+    t.tickets = t.hist + MAX_PASSES * RADIX;
+    t.status = t.tickets + 32;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- 1. all-pass histogram --------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sort_histogram_kernel(const uint64_t* __restrict__ keys, int64_t n, int passes, int end_bit, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = keys[i];
+        for (int p = 0; p < passes; ++p) {
+            const int shift = p * RADIX_BITS;
+            const int bits = min(RADIX_BITS, end_bit - shift);
+            const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
+            atomicAdd(&sh[p * RADIX + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
+        const uint32_t v = sh[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// ---- 2. exclusive scan of each pass's 256 bins --------------------------------------------
+__global__ void __launch_bounds__(RADIX) sort_scan_hist_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t warp_tot[RADIX / 32];
+    uint32_t* h = hist + blockIdx.x * RADIX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = h[tid];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    h[tid] = base + incl - v;
+}
+
+// ---- 3. one onesweep pass -------------------------------------------------------------------
+struct __align__(16) PassSmem {
+    uint64_t keys[SORT_TILE];
+    uint32_t vals[SORT_TILE];
+    uint32_t warp_cnt[SORT_WARPS][RADIX];
+    uint32_t digit_excl[RADIX];
+    uint32_t global_base[RADIX];
+    uint32_t warp_tot[RADIX / 32];
+    uint32_t block_id;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+                     const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t dmask = (1u << bits) - 1u;
+
+    if (tid == 0) sm.block_id = atomicAdd(ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t block = sm.block_id;
+    const int64_t tile_base = block * SORT_TILE;
+    const int count = (int)min((int64_t)SORT_TILE, n - tile_base);
+
+    // -- load (warp-striped: lane l, item j <-> element warp*512 + j*32 + l; order-preserving)
+    uint64_t k[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+    const int wbase = warp * (32 * SORT_ITEMS);
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const int li = wbase + j * 32 + lane;
+        k[j] = li < count ? keys_in[tile_base + li] : ~0ull;
+    }
+    // -- stable rank inside the warp's digit streams
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const int li = wbase + j * 32 + lane;
+        const bool valid = li < count;
+        const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        uint32_t r = 0;
+        if (valid) {
+            const uint32_t peers = __match_any_sync(vmask, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t c = 0;
+            if (lane == leader) {
+                c = sm.warp_cnt[warp][d];
+                sm.warp_cnt[warp][d] = c + __popc(peers);
+            }
+            c = __shfl_sync(peers, c, leader);
+            r = c + __popc(peers & lt_mask);
+        }
+        rank[j] = r;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // -- per digit (thread == digit): warp bases, CTA total, look-back
+    {
+        const int d = tid;
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = sm.warp_cnt[w][d];
+            sm.warp_cnt[w][d] = tot;
+            tot += t;
+        }
+        // CTA-local exclusive scan over digits (placement inside the staged tile)
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t dbase = 0;
+        for (int w = 0; w < warp; ++w) dbase += sm.warp_tot[w];
+        const uint32_t excl = dbase + incl - tot;
+        sm.digit_excl[d] = excl;
+
+        // decoupled look-back for this digit
+        uint32_t* my = status + (size_t)block * RADIX + d;
+        uint32_t prev = 0;
+        if (block == 0) {
+            st_volatile(my, FLAG_PREFIX | tot);
+        } else {
+            st_volatile(my, FLAG_AGG | tot);
+            int64_t b = block - 1;
+            unsigned spins = 0;
+            while (true) {
+                const uint32_t s = ld_volatile(status + (size_t)b * RADIX + d);
+                const uint32_t f = s & ~VALUE_MASK;
+                if (f == 0) {
+                    if (++spins > (1u << 26)) __trap();   // fail loudly rather than hang the GPU
+                    continue;
+                }
+                prev += s & VALUE_MASK;
+                if (f == FLAG_PREFIX) break;
+                --b;
+            }
+            st_volatile(my, FLAG_PREFIX | (prev + tot));
+        }
+        sm.global_base[d] = digit_base[d] + prev - excl;
+    }
+    __syncthreads();
+
+    // -- stage the tile in sorted order
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const int li = wbase + j * 32 + lane;
+        if (li < count) {
+            const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
+            const uint32_t pos = sm.digit_excl[d] + sm.warp_cnt[warp][d] + rank[j];
+            sm.keys[pos] = k[j];
+            sm.vals[pos] = vals_in[tile_base + li];
+        }
+    }
+    __syncthreads();
+
+    // -- coalesced write-out of digit runs
+    for (int i = tid; i < count; i += SORT_THREADS) {
+        const uint64_t key = sm.keys[i];
+        const uint32_t d = (uint32_t)(key >> shift) & dmask;
+        const size_t dst = (size_t)sm.global_base[d] + i;
+        keys_out[dst] = key;
+        vals_out[dst] = sm.vals[i];
+    }
+}
+
+}  // namespace
+
+size_t sort_temp_bytes(int64_t n) {
+    const size_t blocks = (size_t)sort_blocks(n > 0 ? n : 1);
+    return sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)MAX_PASSES * blocks * RADIX) + 256;
+}
+
+int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                      cudaStream_t s) {
+    if (end_bit < 1 || end_bit > 64) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (n >= (int64_t)VALUE_MASK) { set_error("sort: n too large"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (n <= 0) return 0;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (passes > MAX_PASSES) { set_error("sort: too many passes"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (temp_bytes < sort_temp_bytes(n)) { set_error("sort: temp too small"); return GLIC_ERR_WORKSPACE; }
+    const int64_t blocks = sort_blocks(n);
+    SortTemp t = carve_sort_temp(temp);
+    const size_t used = sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)passes * blocks * RADIX);
+    GLIC_CUDA_TRY(cudaMemsetAsync(temp, 0, used, s));
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PassSmem)));
+        attr_set = true;
+    }
+    int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
+    sort_histogram_kernel<<<hist_blocks, 256, 0, s>>>(keys[0], n, passes, end_bit, t.hist);
+    GLIC_LAUNCH_CHECK();
+    sort_scan_hist_kernel<<<passes, RADIX, 0, s>>>(t.hist);
+    GLIC_LAUNCH_CHECK();
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * RADIX_BITS;
+        const int bits = min(RADIX_BITS, end_bit - shift);
+        onesweep_pass_kernel<<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem), s>>>(
+            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, bits, t.hist + p * RADIX,
+            t.status + (size_t)p * blocks * RADIX, t.tickets + p);
+        GLIC_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    return cur;
+}
+
+}  // namespace glic

@@ -1,0 +1,373 @@
+// render.cu -- tile ranges, bucket offsets, per-tile front-to-back blend (forward) and the
+// per-splat ("bucketed") backward.
+//
+// Replaces identifyTileRanges + perTileBucketCount + InclusiveSum (reference
+// rasterizer_impl.cu:195-231,426-442), renderCUDA (forward.cu:321-481) incl. the D2D colour
+// copy (rasterizer_impl.cu:471), and PerGaussianRenderCUDA (backward.cu:379-597).
+//
+// Design notes (ours):
+//   * splat data of a batch is gathered ONCE per tile from the 48-byte records into shared
+//     memory (xy, conic, opacity AND rgb -- the reference re-gathers rgb from global memory for
+//     every contributing pixel-splat pair);
+//   * each staged splat carries an 8-bit "row-pair" mask: warp w (rows 2w,2w+1 of the tile)
+//     skips, warp-uniformly, splats whose alpha>=1/255 ellipse cannot reach its rows.  The mask
+//     is conservative, so results are bit-identical to evaluating every pair;
+//   * checkpoints are one float4 (T, C.r, C.g, C.b) per pixel per 32-splat bucket -> 16-byte
+//     coalesced stores / loads;
+//   * the final colour is written to the caller's image and to the saved-state copy by the same
+//     kernel (no separate D2D copy);
+//   * backward runs exactly one warp per non-empty bucket, 8 buckets per CTA, and feeds the
+//     shuffle pipeline from a warp-private shared-memory slab filled with coalesced loads.
+// The per-pixel arithmetic (power, alpha, T, C) keeps the reference's operation order through the
+// fixed-order intrinsics of geom_math.cuh, so colours/transmittance agree bit-for-bit with the
+// reference build on the same sorted list.
+#include "geom_math.cuh"
+
+namespace glic {
+
+// ---- tile ranges -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys, uint32_t T, uint2* __restrict__ ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t cur = (uint32_t)(keys[i] >> 32);
+    if (cur >= T) return;
+    if (i == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (cur != prev) {
+            if (prev < T) ranges[prev].y = (uint32_t)i;
+            ranges[cur].x = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[cur].y = (uint32_t)R;
+}
+
+// bucket_offsets = inclusive scan of ceil(n_t / 32); single CTA (T is a few thousand).
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ bucket_offsets, ImageHeader* hdr,
+                   long long R, int buckets) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        uint32_t v = 0;
+        if (t < T && buckets) { const uint2 r = ranges[t]; v = (r.y - r.x + BUCKET - 1) / BUCKET; }
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_tot[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t out = carry + warp_tot[warp] + incl;
+        if (t < T) bucket_offsets[t] = out;
+        __syncthreads();
+        if (tid == 1023) carry = out;
+        __syncthreads();
+    }
+    if (tid == 0) { hdr->num_buckets = carry; hdr->num_rendered = R; }
+}
+
+// ---- forward blend -------------------------------------------------------------------------
+struct __align__(8) StagedTail { float blue; uint32_t rowmask; };
+
+__global__ void __launch_bounds__(TILE_PIX)
+render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
+                      const uint32_t* __restrict__ bucket_offsets, uint32_t* __restrict__ bucket_to_tile,
+                      float4* __restrict__ ckpt, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
+                      float* __restrict__ pixel_colors, float* __restrict__ out_color, float* __restrict__ out_T) {
+    __shared__ float4 s_a[TILE_PIX];        // x, y, conic.x, conic.y
+    __shared__ float4 s_b[TILE_PIX];        // conic.z, opacity, red, green
+    __shared__ StagedTail s_c[TILE_PIX];    // blue, row-pair mask
+    __shared__ uint32_t s_red[TILE_PIX / 32];
+
+    const int tid = threadIdx.y * TILE + threadIdx.x;
+    const int warp = tid >> 5;
+    const uint32_t tile = blockIdx.y * vp.grid_x + blockIdx.x;
+    const int pix_min_x = blockIdx.x * TILE, pix_min_y = blockIdx.y * TILE;
+    const int px = pix_min_x + threadIdx.x, py = pix_min_y + threadIdx.y;
+    const bool inside = px < vp.W && py < vp.H;
+    const float pfx = (float)px, pfy = (float)py;
+    const size_t pid = (size_t)py * vp.W + px;
+    const uint2 range = ranges[tile];
+    const int n_splats = (int)(range.y - range.x);
+    const int rounds = (n_splats + TILE_PIX - 1) / TILE_PIX;
+
+    uint32_t bbm = 0;
+    if (!no_color) {
+        bbm = tile == 0 ? 0u : bucket_offsets[tile - 1];
+        const int nb = (n_splats + BUCKET - 1) / BUCKET;
+        for (int b = tid; b < nb; b += TILE_PIX) bucket_to_tile[bbm + b] = tile;
+    }
+    // rows of this warp (two tile rows) for the conservative row-pair cull
+    const uint32_t warp_bit = 1u << warp;
+    const float tile_y0 = (float)pix_min_y;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last_contributor = 0;
+
+    for (int i = 0; i < rounds; ++i) {
+        if (__syncthreads_count(done) == TILE_PIX) break;
+        const int progress = i * TILE_PIX + tid;
+        if (progress < n_splats) {
+            const uint32_t id = point_list[range.x + progress];
+            const float4 r0 = rec[3 * (size_t)id + 0];
+            const float4 r1 = rec[3 * (size_t)id + 1];
+            const float4 r2 = rec[3 * (size_t)id + 2];
+            // conservative vertical half-extent of {alpha >= 1/255}: dy^2 <= 2*thr*cx/det(conic);
+            // falls back to the (looser) 3.33-sigma bound from the radius when det cancels badly.
+            const float thr = __logf(255.0f * r1.y) + 1e-3f;
+            const float prod = r0.z * r1.x;
+            const float det = prod - r0.w * r0.w;
+            float hy = 1.11f * (float)__float_as_int(r2.z) + 1.0f;
+            if (det > 1e-3f * prod) hy = fminf(hy, sqrtf(2.0f * thr * r0.z / det) * 1.001f + 0.01f);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int w = 0; w < TILE_PIX / 32; ++w) {
+                const float row_lo = tile_y0 + (float)(2 * w), row_hi = row_lo + 1.0f;
+                if (!(row_lo > r0.y + hy || row_hi < r0.y - hy)) mask |= 1u << w;
+            }
+            s_a[tid] = r0;
+            s_b[tid] = r1;
+            StagedTail tl; tl.blue = r2.x; tl.rowmask = mask;
+            s_c[tid] = tl;
+        }
+        __syncthreads();
+        const int nb = min(TILE_PIX, n_splats - i * TILE_PIX);
+        if (!done) {
+            for (int j = 0; j < nb; ++j) {
+                if ((j & (BUCKET - 1)) == 0 && !no_color) {           // checkpoint every 32 splats
+                    ckpt[(size_t)bbm * TILE_PIX + tid] = make_float4(T, C0, C1, C2);
+                    ++bbm;
+                }
+                const StagedTail tl = s_c[j];
+                if (!(tl.rowmask & warp_bit)) continue;               // warp-uniform skip
+                const float4 a = s_a[j];
+                const float4 b = s_b[j];
+                const float dx = fsub(a.x, pfx), dy = fsub(a.y, pfy);
+                const float power = splat_power(dx, dy, a.z, a.w, b.x);
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, fmul(b.y, expf(power)));
+                if (alpha < (1.0f / 255.0f)) continue;
+                const float test_T = fmul(T, fsub(1.0f, alpha));
+                if (test_T < 0.0001f) { done = true; break; }
+                if (!no_color) {
+                    C0 = ffma(T, fmul(alpha, b.z), C0);
+                    C1 = ffma(T, fmul(alpha, b.w), C1);
+                    C2 = ffma(T, fmul(alpha, tl.blue), C2);
+                }
+                T = test_T;
+                last_contributor = (uint32_t)(i * TILE_PIX + j + 1);
+            }
+        }
+    }
+
+    if (inside) {
+        out_T[pid] = T;
+        if (!no_color) {
+            const size_t HW = (size_t)vp.W * vp.H;
+            n_contrib[pid] = last_contributor;
+            out_color[pid] = C0; out_color[HW + pid] = C1; out_color[2 * HW + pid] = C2;
+            pixel_colors[pid] = C0; pixel_colors[HW + pid] = C1; pixel_colors[2 * HW + pid] = C2;
+        }
+    }
+    if (no_color) return;
+    uint32_t m = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) s_red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t mm = 0;
+#pragma unroll
+        for (int w = 0; w < TILE_PIX / 32; ++w) mm = max(mm, s_red[w]);
+        max_contrib[tile] = mm;
+    }
+}
+
+// ---- per-splat backward --------------------------------------------------------------------
+constexpr int BWD_WARPS = 8;
+
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+render_backward_kernel(ViewParams vp, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
+                       const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
+                       const uint32_t* __restrict__ bucket_offsets, const uint32_t* __restrict__ bucket_to_tile,
+                       const float4* __restrict__ ckpt, const uint32_t* __restrict__ n_contrib,
+                       const uint32_t* __restrict__ max_contrib, const float* __restrict__ pixel_colors,
+                       const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
+    __shared__ float s_pix[BWD_WARPS][8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bucket = blockIdx.x * BWD_WARPS + warp;
+    if (bucket >= hdr->num_buckets) return;                     // warp-uniform
+
+    const uint32_t tile = bucket_to_tile[bucket];
+    const uint2 range = ranges[tile];
+    const int n_splats = (int)(range.y - range.x);
+    const uint32_t bbm = tile == 0 ? 0u : bucket_offsets[tile - 1];
+    const int bucket_in_tile = (int)(bucket - bbm);
+    const int splat_in_tile = bucket_in_tile * BUCKET + lane;
+    const bool valid_splat = splat_in_tile < n_splats;
+    if ((uint32_t)(bucket_in_tile * BUCKET) >= max_contrib[tile]) return;   // nobody got this far
+
+    uint32_t gid = 0;
+    float mx = 0.f, my = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (valid_splat) {
+        gid = point_list[range.x + splat_in_tile];
+        const float4 r0 = rec[3 * (size_t)gid + 0];
+        const float4 r1 = rec[3 * (size_t)gid + 1];
+        const float4 r2 = rec[3 * (size_t)gid + 2];
+        mx = r0.x; my = r0.y; cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
+    }
+    const int tile_x = tile % vp.grid_x, tile_y = tile / vp.grid_x;
+    const int pix_min_x = tile_x * TILE, pix_min_y = tile_y * TILE;
+    const size_t HW = (size_t)vp.W * vp.H;
+    const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
+    const float4* ck = ckpt + (size_t)bucket * TILE_PIX;
+    float (*sp)[32] = s_pix[warp];
+
+    float acc_mx = 0.f, acc_my = 0.f, acc_cx = 0.f, acc_cy = 0.f, acc_cw = 0.f, acc_o = 0.f;
+    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
+    float T = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    int nc = 0;
+
+    for (int i = 0; i < TILE_PIX + 31; ++i) {
+        if ((i & 31) == 0 && i < TILE_PIX) {
+            // coalesced fill of the next 32 pixels' state: lane l <-> pixel i + l of the tile
+            __syncwarp();
+            const int p = i + lane;
+            const int qx = pix_min_x + (p & (TILE - 1)), qy = pix_min_y + (p >> 4);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f;
+            int n = 0;
+            if (qx < vp.W && qy < vp.H) {
+                const size_t q = (size_t)qy * vp.W + qx;
+                n = (int)n_contrib[q];
+                if (n > bucket_in_tile * BUCKET) {               // pixel reached this bucket: checkpoint is valid
+                    const float4 k4 = ck[p];
+                    v0 = k4.x;
+                    v1 = k4.y - pixel_colors[q];
+                    v2 = k4.z - pixel_colors[HW + q];
+                    v3 = k4.w - pixel_colors[2 * HW + q];
+                    v4 = dL_dpix[q]; v5 = dL_dpix[HW + q]; v6 = dL_dpix[2 * HW + q];
+                } else {
+                    n = 0;
+                }
+            }
+            sp[0][lane] = v0; sp[1][lane] = v1; sp[2][lane] = v2; sp[3][lane] = v3;
+            sp[4][lane] = v4; sp[5][lane] = v5; sp[6][lane] = v6; sp[7][lane] = __int_as_float(n);
+            __syncwarp();
+        }
+        // hand the running state to the next splat (lane+1), which treats the same pixel next
+        T = __shfl_up_sync(0xffffffffu, T, 1);
+        ar0 = __shfl_up_sync(0xffffffffu, ar0, 1);
+        ar1 = __shfl_up_sync(0xffffffffu, ar1, 1);
+        ar2 = __shfl_up_sync(0xffffffffu, ar2, 1);
+        g0 = __shfl_up_sync(0xffffffffu, g0, 1);
+        g1 = __shfl_up_sync(0xffffffffu, g1, 1);
+        g2 = __shfl_up_sync(0xffffffffu, g2, 1);
+        nc = __shfl_up_sync(0xffffffffu, nc, 1);
+        if (lane == 0) {
+            if (i < TILE_PIX) {
+                const int s = i & 31;
+                T = sp[0][s]; ar0 = sp[1][s]; ar1 = sp[2][s]; ar2 = sp[3][s];
+                g0 = sp[4][s]; g1 = sp[5][s]; g2 = sp[6][s]; nc = __float_as_int(sp[7][s]);
+            } else {
+                nc = 0;
+            }
+        }
+        const int p = i - lane;
+        if (valid_splat && p >= 0 && p < TILE_PIX && splat_in_tile < nc) {
+            const float pfx = (float)(pix_min_x + (p & (TILE - 1))), pfy = (float)(pix_min_y + (p >> 4));
+            const float dx = fsub(mx, pfx), dy = fsub(my, pfy);
+            const float power = splat_power(dx, dy, cx, cy, cz);
+            if (power > 0.0f) continue;
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, fmul(op, G));
+            if (alpha < (1.0f / 255.0f)) continue;
+            const float dchannel_dcolor = alpha * T;
+            const float alpha_inverse = 1.0f / (1.0f - alpha);
+            float dL_dalpha;
+            ar0 += T * alpha * c0; acc_c0 += dchannel_dcolor * g0; dL_dalpha = ((c0 * T) - alpha_inverse * (-ar0)) * g0;
+            ar1 += T * alpha * c1; acc_c1 += dchannel_dcolor * g1; dL_dalpha += ((c1 * T) - alpha_inverse * (-ar1)) * g1;
+            ar2 += T * alpha * c2; acc_c2 += dchannel_dcolor * g2; dL_dalpha += ((c2 * T) - alpha_inverse * (-ar2)) * g2;
+            T = fmul(T, fsub(1.0f, alpha));
+            const float dL_dG = op * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * cx - gdy * cy;
+            const float dG_ddely = -gdy * cz - gdx * cy;
+            acc_mx += dL_dG * dG_ddelx * ddelx_dx;
+            acc_my += dL_dG * dG_ddely * ddely_dy;
+            acc_cx += -0.5f * gdx * dx * dL_dG;
+            acc_cy += -0.5f * gdx * dy * dL_dG;
+            acc_cw += -0.5f * gdy * dy * dL_dG;
+            acc_o += G * dL_dalpha;
+        }
+    }
+    if (valid_splat) {
+        atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx);
+        atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my);
+        atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx);
+        atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy);
+        atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw);
+        atomicAdd(&dL_dopacity[gid], acc_o);
+        atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], acc_c0);
+        atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], acc_c1);
+        atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], acc_c2);
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+int launch_tile_ranges(int64_t R, const uint64_t* keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s) {
+    GLIC_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, s));
+    if (R > 0) {
+        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, (uint32_t)T, img.ranges);
+        GLIC_LAUNCH_CHECK();
+    }
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(T, img.ranges, img.bucket_offsets, img.hdr, (long long)R, buckets ? 1 : 0);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* point_list, GeomState g, ImageState img,
+                          SampleState smp, float* out_color, float* out_final_T, cudaStream_t s) {
+    dim3 grid(vp.grid_x, vp.grid_y), block(TILE, TILE);
+    render_forward_kernel<<<grid, block, 0, s>>>(vp, no_color, img.ranges, point_list, g.rec, img.bucket_offsets,
+                                                 smp.bucket_to_tile, smp.ckpt,
+                                                 img.n_contrib, img.max_contrib, img.pixel_colors, out_color,
+                                                 out_final_T);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,
+                           ImageState img, SampleState smp, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                           float* dL_dopacity, float* dL_dcolors, cudaStream_t s) {
+    (void)P;
+    if (max_buckets <= 0) return GLIC_OK;
+    const unsigned blocks = (unsigned)((max_buckets + BWD_WARPS - 1) / BWD_WARPS);
+    render_backward_kernel<<<blocks, BWD_WARPS * 32, 0, s>>>(
+        vp, img.hdr, img.ranges, point_list, g.rec, img.bucket_offsets, smp.bucket_to_tile,
+        smp.ckpt, img.n_contrib, img.max_contrib, img.pixel_colors, dL_dpix,
+        dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+}  // namespace glic

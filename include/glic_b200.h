@@ -1,0 +1,191 @@
+/*
+ * glic_b200.h -- C ABI of the B200-native (sm_100a) Gaussian rasterizer hot path.
+ *
+ * Drop-in boundary for Gaussian-LIC (APRIL-ZJU/Gaussian-LIC @ 4566e6e).  Every entry point
+ * replaces one raw-pointer interface of the reference; the LibTorch symbols the SLAM code
+ * actually links against (RasterizeGaussiansCUDA, RasterizeGaussiansBackwardCUDA, adamUpdate,
+ * fusedssim, fusedssim_backward, distCUDA2) are thin shims over this ABI
+ * (gaussian_lic_b200/csrc/torch_shim.cpp).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions across the ABI.
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     the reference uses for every launch).
+ *   - the library never allocates device memory: the caller provides workspaces whose sizes
+ *     come from the glic_*_bytes() queries (replaces the reference's four
+ *     std::function<char*(size_t)> resize callbacks, rasterizer.h:29-34).
+ *   - return value: GLIC_OK (0) or a negative glic_status; glic_last_error() gives text.
+ *   - all floating point is IEEE fp32; indices are 32-bit, keys 64-bit.
+ *
+ * Reference citations are relative to /root/reference/src/.
+ */
+#ifndef GLIC_B200_H_INCLUDED
+#define GLIC_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLIC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GLIC_API __attribute__((visibility("default")))
+#else
+#define GLIC_API
+#endif
+
+typedef enum glic_status {
+    GLIC_OK = 0,
+    GLIC_ERR_INVALID_ARGUMENT = -1, /* bad shape / null pointer / unsupported degree        */
+    GLIC_ERR_WORKSPACE = -2,        /* a workspace is smaller than glic_*_bytes() requires   */
+    GLIC_ERR_CUDA = -3,             /* a CUDA runtime call failed (text in glic_last_error)  */
+    GLIC_ERR_NO_DEVICE = -4         /* no CUDA device / wrong architecture                   */
+} glic_status;
+
+/* Tile geometry is part of the parity contract (rasterizer/cuda_rasterizer/config.h:16-17). */
+#define GLIC_TILE 16
+#define GLIC_BUCKET 32 /* checkpoint period of the per-splat backward (forward.cu:412) */
+
+GLIC_API const char* glic_last_error(void);
+GLIC_API int glic_abi_version(void);
+
+/* Per-view camera block, all DEVICE pointers except the scalars.
+ * view/proj: 16 floats each, column-major Rt and P*Rt exactly as the reference's kernels get
+ * them (rasterize_points.cu:129-130, camera.h:60,86,109).  campos: 3 floats. */
+typedef struct glic_view {
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy;
+    float limx_neg, limx_pos, limy_neg, limy_pos; /* camera.h:63-66 */
+    int width, height;
+} glic_view;
+
+/* ---------------------------------------------------------------------------------------
+ * Workspace sizes.  Replaces required<GeometryState/ImageState/BinningState/SampleState>()
+ * (rasterizer/cuda_rasterizer/rasterizer_impl.h:92-108, rasterizer_impl.cu:233-291).
+ * The four buffers are opaque and may be round-tripped by the caller between forward and
+ * backward (rasterizer.cpp:83-98 saves them in the autograd context).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_geom_bytes(int P);
+GLIC_API size_t glic_image_bytes(int width, int height);
+GLIC_API size_t glic_binning_bytes(int64_t num_rendered);
+GLIC_API size_t glic_sample_bytes(int64_t num_rendered, int width, int height); /* upper bound on buckets */
+GLIC_API int64_t glic_max_buckets(int64_t num_rendered, int width, int height);
+
+/* ---------------------------------------------------------------------------------------
+ * Forward, stage 1: per-Gaussian preprocess + tile counting + prefix sum.
+ * Replaces FORWARD::preprocess + cub::DeviceScan::InclusiveSum + the D2H read of
+ * num_rendered (rasterizer_impl.cu:362-398; forward.cu:232-319).
+ *   means3D[P,3] scales[P,3] rotations[P,4] opacities[P] dc[P,3] sh[P,M,3]: activated inputs
+ *   (rasterize_points.h:25-50).  sh may be NULL when M == 0.
+ *   radii[P] (int32) is written for every Gaussian (0 = culled).
+ *   *num_rendered_host receives R (the call synchronises `stream` once, exactly where the
+ *   reference does its blocking cudaMemcpy at rasterizer_impl.cu:398).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, const float* scales,
+                            float scale_modifier, const float* rotations, const float* opacities,
+                            const float* dc, const float* sh, const glic_view* view, int no_color,
+                            int* radii, void* geom_ws, size_t geom_bytes, void* image_ws,
+                            size_t image_bytes, int64_t* num_rendered_host, void* stream);
+
+/* Forward, stage 2: key emission, stable radix sort of (tile|depth) keys, tile ranges, bucket
+ * offsets, per-tile front-to-back blend.  Replaces duplicateWithKeys, cub::DeviceRadixSort,
+ * identifyTileRanges, perTileBucketCount, the second InclusiveSum + D2H read, FORWARD::render
+ * and the D2D copy of the colour image (rasterizer_impl.cu:400-473; forward.cu:321-481).
+ *   out_color[3,H,W], out_final_T[H,W]; no background term (forward.cu:466-467).
+ *   *num_buckets_host receives B when non-NULL (costs one stream sync; pass NULL to stay
+ *   asynchronous -- backward only needs the value stored inside image_ws).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_forward_render(int P, const glic_view* view, int no_color, int64_t num_rendered,
+                        void* geom_ws, void* image_ws, void* binning_ws, size_t binning_bytes,
+                        void* sample_ws, size_t sample_bytes, float* out_color, float* out_final_T,
+                        int64_t* num_buckets_host, void* stream);
+
+/* Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:476-580;
+ * backward.cu:138-597) AND the ten torch::zeros of rasterize_points.cu:192-201: every output
+ * element is written (exact zeros for culled Gaussians), nothing needs pre-zeroing.
+ *   dL_dpix[3,H,W]; outputs shaped as RasterizeGaussiansBackwardCUDA's tensors
+ *   (rasterize_points.h:52-82): dL_dmeans2D[P,3] (NDC-scaled, .z = 0), dL_dcolors[P,3],
+ *   dL_dopacity[P], dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_ddc[P,3], dL_dsh[P,M,3],
+ *   dL_dscales[P,3], dL_drotations[P,4].  dL_dconic[P,4] (x,y,0,w) is scratch and may alias
+ *   nothing else.  Gradients are w.r.t. the ACTIVATED inputs.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_backward(int P, int sh_degree, int M, const float* means3D, const float* scales,
+                  float scale_modifier, const float* rotations, const float* dc, const float* sh,
+                  const glic_view* view, const int* radii, int64_t num_rendered, const void* geom_ws,
+                  const void* binning_ws, const void* image_ws, const void* sample_ws,
+                  const float* dL_dpix, float lambda_erank, float* dL_dmeans2D, float* dL_dconic,
+                  float* dL_dopacity, float* dL_dcolors, float* dL_dmeans3D, float* dL_dcov3D,
+                  float* dL_ddc, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, end_bit).
+ * Replaces cub::DeviceRadixSort::SortPairs<uint64,uint32>(begin_bit=0, end_bit)
+ * (rasterizer_impl.cu:419-424).  Own onesweep implementation, no CUB.
+ * Result lands in keys_out/vals_out; keys_in/vals_in are clobbered (used as ping-pong).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_sort_temp_bytes(int64_t n);
+GLIC_API int glic_sort_pairs_u64_u32(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
+                            uint64_t* keys_out, uint32_t* vals_out, void* temp, size_t temp_bytes,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Visibility-masked Adam.  Replaces ADAM::adamUpdate (rasterizer/cuda_rasterizer/adam.cu:9-67,
+ * adam.h:12-23).  In place on param / exp_avg / exp_avg_sq; element j belongs to Gaussian j/M;
+ * no bias correction.  `visible` is N bytes (bool).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_adam_update(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     const uint8_t* visible, float lr, float b1, float b2, float eps, uint32_t N,
+                     uint32_t M, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused SSIM.  Replaces fusedssimCUDA / fusedssim_backwardCUDA (fused-ssim/ssim.cu:186-365).
+ * img*: [B,CH,H,W] contiguous.  Partial-derivative maps may be NULL in forward (train = false).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_fused_ssim(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2,
+                    float* ssim_map, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream);
+GLIC_API int glic_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, const float* img1,
+                             const float* img2, const float* dL_dmap, const float* dm_dmu1,
+                             const float* dm_dsigma1_sq, const float* dm_dsigma12, float* dL_dimg1,
+                             void* stream);
+
+/* Whole photometric loss of one mapping iteration in two launches (gaussian.cpp:685-691,
+ * loss_utils.h:30-33,189-193): L = (1-lambda)*mean|img-gt| + lambda*(1-mean(SSIM)), and
+ * dL/dimg.  loss_out: 1 device float (accumulated; zeroed by the call).  scratch: 3*CH*H*W floats. */
+GLIC_API size_t glic_loss_scratch_bytes(int CH, int H, int W);
+GLIC_API int glic_l1_ssim_loss(int CH, int H, int W, float lambda_dssim, const float* img, const float* gt,
+                      float* loss_out, float* dL_dimg, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * simple-knn.  Replaces SimpleKNN::knn (simple-knn/simple_knn.cu:185-221): mean of the three
+ * smallest squared distances to other points.  points[P,3] -> mean_dists[P].
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_knn_temp_bytes(int P);
+GLIC_API int glic_knn_mean_dist2(int P, const float* points, float* mean_dists, void* temp, size_t temp_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Introspection for parity tests (copies internal state to caller DEVICE buffers; any pointer
+ * may be NULL).  Shapes: depth[P] xy[P,2] conic_opacity[P,4] rgb[P,3] tiles_touched[P]
+ * offsets[P] clamped[P,3] (u8) | point_list[R] keys_sorted[R] | ranges[T,2] bucket_offsets[T]
+ * n_contrib[H*W] max_contrib[T].
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_debug_geom(int P, const void* geom_ws, float* depth, float* xy, float* conic_opacity, float* rgb,
+                    uint32_t* tiles_touched, uint32_t* offsets, uint8_t* clamped, void* stream);
+GLIC_API int glic_debug_binning(int64_t num_rendered, const void* binning_ws, uint32_t* point_list,
+                       uint64_t* keys_sorted, void* stream);
+GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint32_t* ranges, uint32_t* bucket_offsets,
+                     uint32_t* n_contrib, uint32_t* max_contrib, int64_t* counters2_host /* {R,B}, HOST pointer */, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+GLIC_API uint64_t glic_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIC_B200_H_INCLUDED */

@@ -1,0 +1,103 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/glic_b200.h declares, sizes behave, and argument validation fails loudly (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "glic_b200.h")).read()
+    return sorted(set(re.findall(r"^GLIC_API [^\n(]*?\b(glic_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gaussian_lic_b200 import capi
+    names = _declared()
+    assert len(names) >= 23
+    for n in names:
+        assert hasattr(capi.lib, n), "libglic_b200.so does not export %s" % n
+    assert set(capi.SYMBOLS) == set(names), set(capi.SYMBOLS) ^ set(names)
+    assert capi.lib.glic_abi_version() == 1
+
+
+def test_torch_shim_exports_reference_symbols():
+    """The LibTorch shim must define the reference's C++ symbols (rasterize_points.h, ssim.h, spatial.h)."""
+    import subprocess
+    so = os.path.join(ROOT, "gaussian_lic_b200", "glic_b200_torch.so")
+    assert os.path.isfile(so), "build with python gaussian_lic_b200/build.py --torch"
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", so], capture_output=True, text=True).stdout
+    for sym in ("RasterizeGaussiansCUDA(", "RasterizeGaussiansBackwardCUDA(", "adamUpdate(", "fusedssim(",
+                "fusedssim_backward(", "distCUDA2("):
+        assert sym in out, sym
+
+
+def test_workspace_sizes_and_bucket_bound():
+    from gaussian_lic_b200 import capi
+    lib = capi.lib
+    assert lib.glic_geom_bytes(0) > 0
+    assert lib.glic_geom_bytes(1000) >= 1000 * (48 + 4 + 1)
+    assert lib.glic_geom_bytes(2000) > lib.glic_geom_bytes(1000)
+    assert lib.glic_image_bytes(1920, 1080) >= 1920 * 1080 * 16
+    assert lib.glic_binning_bytes(10 ** 6) >= 10 ** 6 * 24
+    T = 120 * 68
+    for R in (0, 1, 31, 32, 33, 5000, 2 * 10 ** 6):
+        mb = lib.glic_max_buckets(R, 1920, 1080)
+        assert mb == R // 32 + min(T, R)
+        assert lib.glic_sample_bytes(R, 1920, 1080) >= mb * (256 * 16 + 4)
+
+
+def test_bucket_bound_property():
+    """B = sum ceil(n_t/32) never exceeds floor(R/32) + min(T, R) (hypothesis)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from gaussian_lic_b200 import capi
+
+    @hyp.given(st.lists(st.integers(0, 5000), min_size=1, max_size=12))
+    @hyp.settings(max_examples=200, deadline=None)
+    def prop(counts):
+        W, H = 64, 48  # 4 x 3 = 12 tiles
+        counts = (counts + [0] * 12)[:12]
+        R = sum(counts)
+        B = sum((c + 31) // 32 for c in counts)
+        assert B <= capi.lib.glic_max_buckets(R, W, H)
+
+    prop()
+
+
+def test_argument_validation_without_gpu():
+    from gaussian_lic_b200 import capi
+    lib = capi.lib
+    R = C.c_int64(-5)
+    rc = lib.glic_forward_preprocess(10, 3, 15, None, None, 1.0, None, None, None, None, None, 0, None, None, 0, None, 0,
+                                     C.byref(R), None)
+    assert rc == -1 and b"view" in lib.glic_last_error()
+    v = capi.View(1, 1, 1, 1.0, 1.0, -1.0, 1.0, -1.0, 1.0, 64, 48)
+    rc = lib.glic_forward_preprocess(10, 7, 15, None, None, 1.0, None, None, None, None, C.byref(v), 0, None, None, 0, None, 0,
+                                     C.byref(R), None)
+    assert rc == -1 and b"sh_degree" in lib.glic_last_error()
+    rc = lib.glic_forward_preprocess(10, 3, 15, None, None, 1.0, None, None, None, None, C.byref(v), 0, None, None, 0, None, 0,
+                                     C.byref(R), None)
+    assert rc == -2 and b"workspace" in lib.glic_last_error()          # image workspace missing
+    rc = lib.glic_forward_preprocess(10, 3, 3, None, None, 1.0, None, None, None, None, C.byref(v), 0, None, None, 0, None, 0,
+                                     C.byref(R), None)
+    assert rc == -1 and b"coefficients" in lib.glic_last_error()       # degree 3 needs M >= 15
+    assert lib.glic_sort_pairs_u64_u32(-1, 45, None, None, None, None, None, 0, None) == -1
+    assert lib.glic_sort_pairs_u64_u32(0, 45, None, None, None, None, None, 0, None) == 0
+    assert lib.glic_adam_update(None, None, None, None, None, 0.1, 0.9, 0.999, 1e-15, 10, 3, None) == -1
+    assert lib.glic_fused_ssim(1, 3, 0, 10, 1e-4, 9e-4, None, None, None, None, None, None, None) == -1
+    assert lib.glic_knn_mean_dist2(0, None, None, None, 0, None) == 0
+    assert lib.glic_knn_mean_dist2(-1, None, None, None, 0, None) == -1
+
+
+def test_package_fails_loudly_without_library(tmp_path, monkeypatch):
+    """No silent CPU/PyTorch fallback: a missing .so is an ImportError."""
+    import importlib
+    from gaussian_lic_b200 import capi
+    monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        capi._load()
+    importlib.reload(capi)

@@ -1,0 +1,137 @@
+"""GPU parity tests of the auxiliary hot-path operators: onesweep sort, fused SSIM / loss, sparse Adam, simple-knn."""
+import numpy as np
+import pytest
+
+from helpers import grad_close
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _sort_check(keys, vals, end_bit):
+    from gaussian_lic_b200 import ops
+    k = torch.as_tensor(keys.view(np.int64)).cuda()
+    v = torch.as_tensor(vals.view(np.int32)).cuda()
+    ko, vo = ops.sort_pairs(k, v, end_bit)
+    torch.cuda.synchronize()
+    mask = np.uint64((1 << end_bit) - 1) if end_bit < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    np.testing.assert_array_equal(ko.cpu().numpy().view(np.uint64), keys[order])
+    np.testing.assert_array_equal(vo.cpu().numpy().view(np.uint32), vals[order])
+
+
+@pytest.mark.parametrize("n", [1, 31, 4096, 4097, 100_003, 1_000_000])
+def test_sort_pairs_tile_depth_keys(n):
+    from gaussian_lic_b200 import synthetic as syn
+    keys, vals = syn.make_sort_pairs(n, seed=99)
+    _sort_check(keys, vals, 45)
+
+
+def test_sort_pairs_stability_and_bit_ranges(oracle32):
+    rng = np.random.default_rng(0)
+    n = 300_000
+    # many duplicate keys: stability is observable through the values
+    keys = rng.integers(0, 50, n, dtype=np.uint64) << np.uint64(7)
+    vals = np.arange(n, dtype=np.uint32)
+    for end_bit in (13, 16, 24, 33, 64):
+        _sort_check(keys | (rng.integers(0, 2 ** 62, n, dtype=np.uint64) << np.uint64(13)), vals, end_bit)
+    _sort_check(keys, vals, 13)
+    # against the C oracle's LSD sort too
+    ko, vo = oracle32.sort_pairs(keys, vals, 13)
+    order = np.argsort(keys & np.uint64((1 << 13) - 1), kind="stable")
+    np.testing.assert_array_equal(vo, vals[order])
+
+
+def test_sort_pairs_full_size_property():
+    """cfg5 size: 50 M pairs -- sortedness + permutation checked on device (no host reference at this size)."""
+    from gaussian_lic_b200 import ops
+    n = 50_000_000
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    tile = torch.randint(0, 8160, (n,), device="cuda", generator=gen, dtype=torch.int64)
+    depth = (torch.rand(n, device="cuda", generator=gen) * 99.8 + 0.2).view(torch.int32).to(torch.int64)
+    keys = (tile << 32) | depth
+    vals = torch.arange(n, device="cuda", dtype=torch.int32)
+    ko, vo = ops.sort_pairs(keys, vals, 45)
+    assert bool((ko[1:] >= ko[:-1]).all())
+    assert bool((keys[vo.long()] == ko).all())                     # values still point at their keys
+    ties = ko[1:] == ko[:-1]
+    assert bool((vo[1:][ties] > vo[:-1][ties]).all())              # stable: ties keep ascending index
+    assert int(vo.long().sum().item()) == n * (n - 1) // 2           # permutation checksum
+
+
+@pytest.mark.parametrize("H,W", [(96, 128), (117, 203)])
+def test_fused_ssim_forward_backward(oracle32, H, W):
+    from gaussian_lic_b200 import ops
+    rng = np.random.default_rng(1)
+    a = rng.random((1, 3, H, W), dtype=np.float32)
+    b = np.clip(a + 0.1 * rng.normal(size=a.shape).astype(np.float32), 0, 1)
+    ta, tb = torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda()
+    m, d1, d2, d3 = ops.fusedssim(ops.SSIM_C1, ops.SSIM_C2, ta, tb, True)
+    om, o1, o2, o3 = oracle32.ssim(a[0], b[0])
+    np.testing.assert_allclose(m.cpu().numpy()[0], om, atol=2e-5)
+    for x, y, n in ((d1, o1, "dm_dmu1"), (d2, o2, "dm_dsigma1_sq"), (d3, o3, "dm_dsigma12")):
+        grad_close(x.cpu().numpy()[0], y, n, rtol=1e-4)
+    dmap = rng.normal(size=a.shape).astype(np.float32)
+    gi = ops.fusedssim_backward(ops.SSIM_C1, ops.SSIM_C2, ta, tb, torch.as_tensor(dmap).cuda(), d1, d2, d3)
+    og = oracle32.ssim_backward(a[0], b[0], dmap[0], o1, o2, o3)
+    grad_close(gi.cpu().numpy()[0], og, "dL_dimg1", rtol=1e-4)
+    m2 = ops.fusedssim(ops.SSIM_C1, ops.SSIM_C2, ta, tb, False)
+    assert m2[1].numel() == 0 and torch.equal(m2[0], m)
+
+
+def test_l1_ssim_loss_matches_oracle(oracle32):
+    from gaussian_lic_b200 import ops, synthetic as syn
+    W, H = 200, 120
+    rng = np.random.default_rng(2)
+    gt = syn.make_gt_image(W, H)
+    img = np.clip(gt + 0.2 * rng.normal(size=gt.shape).astype(np.float32), 0, 1.5).astype(np.float32)
+    r = ops.CRasterizer(W, H)
+    loss, dl = r.loss(torch.as_tensor(img).cuda(), torch.as_tensor(gt).cuda())
+    L, g = oracle32.loss(img, gt)
+    assert abs(float(loss.item()) - L) < 1e-5
+    grad_close(dl.cpu().numpy(), g, "dL_dimg (fused loss)", rtol=1e-4)
+
+
+def test_sparse_adam_matches_oracle(oracle32):
+    from gaussian_lic_b200 import ops
+    rng = np.random.default_rng(3)
+    N = 5000
+    vis = rng.random(N) < 0.7
+    for M, lr in ((3, 1.6e-4), (45, 2.5e-3 / 20), (1, 0.05), (4, 0.001)):
+        p = rng.normal(size=(N, M)).astype(np.float32)
+        gr = rng.normal(size=(N, M)).astype(np.float32) * 1e-3
+        m = rng.normal(size=(N, M)).astype(np.float32) * 1e-3
+        v = (rng.random((N, M)).astype(np.float32)) * 1e-6
+        tp, tg, tm, tv = (torch.as_tensor(x).cuda() for x in (p, gr, m, v))
+        ops.adamUpdate(tp, tg, tm, tv, torch.as_tensor(vis).cuda(), lr, 0.9, 0.999, 1e-15, N, M)
+        op, om, ov = oracle32.adam(p, gr, m, v, vis, lr)
+        np.testing.assert_allclose(tp.cpu().numpy(), op, rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(tm.cpu().numpy(), om, rtol=2e-6, atol=1e-12)
+        np.testing.assert_allclose(tv.cpu().numpy(), ov, rtol=2e-6, atol=1e-15)
+        assert np.array_equal(tp.cpu().numpy()[~vis], p[~vis])     # invisible rows untouched, bit for bit
+
+
+@pytest.mark.parametrize("P", [4, 1000, 5000])
+def test_knn_matches_bruteforce(oracle32, P):
+    from gaussian_lic_b200 import ops
+    rng = np.random.default_rng(P)
+    pts = (rng.normal(size=(P, 3)) * np.array([5.0, 1.0, 3.0]) + 2.0).astype(np.float32)
+    d = ops.distCUDA2(torch.as_tensor(pts).cuda())
+    ref = oracle32.knn(pts)
+    np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=2e-6)
+
+
+def test_knn_skybox_size():
+    """100 k points on a sphere cap (gaussian.cpp:243-262): checked against torch.cdist in chunks."""
+    from gaussian_lic_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    P = 100_000
+    v = torch.randn(P, 3, device="cuda", generator=gen)
+    v[:, 1] = -v[:, 1].abs()
+    pts = 10_000.0 * v / v.norm(dim=1, keepdim=True)
+    d = ops.distCUDA2(pts.contiguous())
+    idx = torch.randint(0, P, (512,), device="cuda", generator=gen)
+    dd = torch.cdist(pts[idx].double(), pts.double()) ** 2
+    dd[torch.arange(512), idx] = float("inf")
+    ref = dd.topk(3, dim=1, largest=False).values.mean(1)
+    torch.testing.assert_close(d[idx].double(), ref, rtol=1e-3, atol=0)

@@ -1,0 +1,124 @@
+"""Known-answer and property tests of the CPU oracle -- no GPU needed."""
+import math
+
+import numpy as np
+import pytest
+
+from gaussian_lic_b200 import synthetic as syn
+
+
+def _one_gaussian(opacity, xyz=(0.0, 0.0, 5.0), scale=0.05, W=64, H=48, f=100.0):
+    g = dict(means=np.array([xyz], np.float32), scales=np.full((1, 3), scale, np.float32),
+             rots=np.array([[1, 0, 0, 0]], np.float32), opacity=np.array([opacity], np.float32),
+             dc=np.array([[1.0, 0.5, -0.2]], np.float32), sh=np.zeros((1, 15, 3), np.float32), degree=0)
+    cam = syn.make_camera(W, H, f, f, W / 2.0, H / 2.0)
+    return g, cam
+
+
+def test_single_isotropic_gaussian_centre_alpha(oracle32):
+    """A Gaussian centred exactly on a pixel: alpha = min(0.99, o), C = alpha * max(0, SH_C0*dc + 0.5)."""
+    # centre projects to ((0+1)*64-1)/2 = 31.5 -> shift by half a pixel so it lands on pixel 32
+    g, cam = _one_gaussian(0.6, xyz=(0.5 * 5.0 / 100.0, 0.5 * 5.0 / 100.0, 5.0))
+    f = oracle32.forward(g, cam)
+    st = oracle32.state(f)
+    np.testing.assert_allclose(st["xy"][0], [32.0, 24.0], atol=1e-4)
+    col = 0.28209479177387814 * g["dc"][0] + 0.5
+    np.testing.assert_allclose(f["color"][:, 24, 32], 0.6 * np.maximum(col, 0), rtol=1e-5)
+    np.testing.assert_allclose(f["final_T"][24, 32], 0.4, rtol=1e-6)
+    assert st["clamped"][0].tolist() == [0, 0, 0]
+    g2, _ = _one_gaussian(1.0, xyz=g["means"][0])
+    f2 = oracle32.forward(g2, cam)
+    np.testing.assert_allclose(f2["final_T"][24, 32], 0.01, rtol=1e-4)      # alpha clamped to 0.99
+    oracle32.free(f); oracle32.free(f2)
+
+
+def test_culls(oracle32):
+    g, cam = _one_gaussian(0.5, xyz=(0, 0, 0.19))
+    f = oracle32.forward(g, cam); assert f["R"] == 0 and f["radii"][0] == 0; oracle32.free(f)      # z <= 0.2
+    g, cam = _one_gaussian(1.0 / 256.0)
+    f = oracle32.forward(g, cam); assert f["R"] == 0 and f["radii"][0] == 0; oracle32.free(f)      # opacity < 1/255
+    g, cam = _one_gaussian(0.5, xyz=(50.0, 0, 5.0))
+    f = oracle32.forward(g, cam); assert f["R"] == 0; oracle32.free(f)                              # off screen
+    assert not f["color"].any() and np.all(f["final_T"] == 1.0)
+
+
+def test_two_gaussians_depth_order(oracle32):
+    g, cam = _one_gaussian(0.5)
+    g = {k: (np.concatenate([v, v]) if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    g["means"][0] = (0.025, 0.025, 6.0); g["means"][1] = (0.02, 0.02, 4.0)     # index 1 is nearer
+    g["dc"][0] = (2.0, 2.0, 2.0); g["dc"][1] = (-1.0, -1.0, -1.0)
+    f = oracle32.forward(g, cam)
+    st = oracle32.state(f)
+    r0, r1 = st["ranges"][24 // 16 * 4 + 32 // 16]
+    assert st["point_list"][r0:r1].tolist() == [1, 0]                          # sorted by depth, not by index
+    oracle32.free(f)
+
+
+def test_contract_properties(oracle32):
+    g, cam = syn.make_scene("cfg1", P=4000)
+    f = oracle32.forward(g, cam)
+    st = oracle32.state(f)
+    assert st["tiles_touched"].sum() == f["R"]
+    k = st["keys_sorted"]
+    assert np.all(k[1:] >= k[:-1])
+    n = (st["ranges"][:, 1] - st["ranges"][:, 0]).astype(np.int64)
+    assert n.sum() == f["R"]
+    assert ((n + 31) // 32).sum() == f["B"] == st["bucket_offsets"][-1]
+    assert f["final_T"].min() >= 1e-4 and f["final_T"].max() <= 1.0
+    assert ((f["radii"] > 0) == (st["tiles_touched"] > 0)).all()
+    # ties inside a tile keep ascending Gaussian index (stable sort)
+    same = k[1:] == k[:-1]
+    assert np.all(st["point_list"][1:][same] > st["point_list"][:-1][same])
+    oracle32.free(f)
+
+
+def test_higher_msb_and_sort(oracle32):
+    assert oracle32.higher_msb(8160) == 13 and oracle32.higher_msb(1200) == 11 and oracle32.higher_msb(1) == 1
+    keys, vals = syn.make_sort_pairs(50_000)
+    ko, vo = oracle32.sort_pairs(keys, vals, 45)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+
+
+def test_ssim_identity_and_padding(oracle32):
+    rng = np.random.default_rng(0)
+    x = rng.random((3, 40, 50), dtype=np.float32)
+    m, *_ = oracle32.ssim(x, x)
+    np.testing.assert_allclose(m, 1.0, atol=1e-5)                             # SSIM(x, x) = 1 everywhere (zero padding included)
+    ones = np.ones((1, 30, 30), np.float32)
+    m, *_ = oracle32.ssim(ones, 0.5 * ones)
+    mu1 = 1.0; mu2 = 0.5                                                       # interior: sigma = 0
+    C1 = np.float32(0.01 ** 2)
+    np.testing.assert_allclose(m[0, 15, 15], (2 * mu1 * mu2 + C1) / (mu1 ** 2 + mu2 ** 2 + C1), rtol=1e-4)
+    assert m[0, 0, 0] != pytest.approx(m[0, 15, 15], rel=1e-3)                # border sees the zero padding
+
+
+def test_adam_closed_form(oracle32):
+    p, g = np.array([[1.0, 2.0]], np.float32), np.array([[0.5, -0.25]], np.float32)
+    z = np.zeros_like(p)
+    p1, m1, v1 = oracle32.adam(p, g, z, z, np.array([1], np.uint8), lr=0.1)
+    np.testing.assert_allclose(m1, 0.1 * g, rtol=1e-6)
+    np.testing.assert_allclose(v1, (1 - np.float32(0.999)) * g * g, rtol=1e-6)   # (1.0f - b2) in fp32, like adam.cu:31
+    np.testing.assert_allclose(p1, p - 0.1 * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-15), rtol=1e-4)   # no bias correction
+    p2, m2, v2 = oracle32.adam(p, g, z, z, np.array([0], np.uint8), lr=0.1)
+    assert np.array_equal(p2, p) and not m2.any() and not v2.any()            # invisible -> untouched
+
+
+def test_knn_regular_grid(oracle32):
+    xs = np.stack(np.meshgrid(np.arange(6.0), np.arange(6.0), np.arange(6.0), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    d = oracle32.knn(xs)
+    np.testing.assert_allclose(d, 1.0, rtol=1e-6)                             # three nearest neighbours at distance 1
+
+
+def test_camera_restatements_agree(oracle32):
+    for v in range(8):
+        R, t = syn.orbit_pose(v)
+        a = syn.make_camera(1920, 1080, 1000.0, 1000.0, 960.0, 540.0, R, t)
+        b = oracle32.camera(1920, 1080, 1000.0, 1000.0, 960.0, 540.0, R, t)
+        for k in ("view", "proj", "campos", "lims"):
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-6)
+        assert a["tanfovx"] == pytest.approx(0.96, rel=1e-6) and a["tanfovy"] == pytest.approx(0.54, rel=1e-6)
+        # every camera of the rig looks at (0,0,10): it projects to the principal point
+        p = np.array([0, 0, 10.0, 1.0])
+        h = a["proj"].reshape(4, 4).T @ p
+        assert abs(h[0] / h[3]) < 1e-5 and abs(h[1] / h[3]) < 1e-5 and h[3] > 0
