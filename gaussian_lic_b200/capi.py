@@ -34,6 +34,8 @@ def _load():
         "glic_last_error": (C.c_char_p, []),
         "glic_abi_version": (i32, []),
         "glic_launch_count": (C.c_uint64, []),
+        "glic_profile_enable": (i32, [i32]),
+        "glic_profile_read": (i32, [C.POINTER(C.c_float), C.POINTER(i32)]),
         "glic_geom_bytes": (sz, [i32]),
         "glic_image_bytes": (sz, [i32, i32]),
         "glic_binning_bytes": (sz, [i64]),
@@ -79,3 +81,19 @@ def ptr(t):
 
 def launch_count():
     return int(lib.glic_launch_count())
+
+
+STAGES = ["preprocess", "emit", "sort", "ranges", "render_fwd", "loss_fwd", "loss_bwd", "render_bwd", "preprocess_bwd",
+          "adam", "zero"]
+
+
+def profile_enable(on=True):
+    check(lib.glic_profile_enable(int(on)), "profile_enable")
+
+
+def profile_read():
+    """-> {stage: (total_ms, count)} since the last profile_enable(True)."""
+    ms = (C.c_float * len(STAGES))()
+    cnt = (C.c_int * len(STAGES))()
+    check(lib.glic_profile_read(ms, cnt), "profile_read")
+    return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(STAGES)}

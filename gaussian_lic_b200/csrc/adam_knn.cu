@@ -221,6 +221,7 @@ extern "C" int glic_adam_update(float* param, const float* grad, float* exp_avg,
     const size_t total = (size_t)N * M;
     if (total == 0) return GLIC_OK;
     const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148u * 32u);
+    StageTimer _t(GLIC_STAGE_ADAM, (cudaStream_t)stream);
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps, N, M);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;

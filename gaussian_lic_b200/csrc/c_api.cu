@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 namespace glic {
 
@@ -11,6 +12,27 @@ static thread_local std::string g_error;
 unsigned long long g_launches = 0;
 
 void set_error(const std::string& s) { g_error = s; }
+
+// ---- stage profiling ----------------------------------------------------------------------
+namespace {
+struct EvPair { cudaEvent_t a, b; };
+bool g_prof = false;
+std::vector<EvPair> g_pairs[GLIC_STAGE_COUNT];
+std::vector<EvPair> g_pool;
+}
+bool profiling_on() { return g_prof; }
+void profile_mark(int stage, bool begin, cudaStream_t s) {
+    if (stage < 0 || stage >= GLIC_STAGE_COUNT) return;
+    if (begin) {
+        EvPair p;
+        if (!g_pool.empty()) { p = g_pool.back(); g_pool.pop_back(); }
+        else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+        cudaEventRecord(p.a, s);
+        g_pairs[stage].push_back(p);
+    } else if (!g_pairs[stage].empty()) {
+        cudaEventRecord(g_pairs[stage].back().b, s);
+    }
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -44,6 +66,25 @@ extern "C" {
 const char* glic_last_error(void) { return g_error.c_str(); }
 int glic_abi_version(void) { return GLIC_ABI_VERSION; }
 uint64_t glic_launch_count(void) { return g_launches; }
+
+int glic_profile_enable(int on) {
+    for (int i = 0; i < GLIC_STAGE_COUNT; ++i) { for (auto& p : g_pairs[i]) g_pool.push_back(p); g_pairs[i].clear(); }
+    g_prof = on != 0;
+    return GLIC_OK;
+}
+int glic_profile_read(float* ms_host, int* count_host) {
+    if (!ms_host || !count_host) { set_error("profile_read: null pointer"); return GLIC_ERR_INVALID_ARGUMENT; }
+    for (int i = 0; i < GLIC_STAGE_COUNT; ++i) {
+        float tot = 0.f; int n = 0;
+        for (auto& p : g_pairs[i]) {
+            if (cudaEventSynchronize(p.b) != cudaSuccess) { cudaGetLastError(); continue; }
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { tot += ms; ++n; } else cudaGetLastError();
+        }
+        ms_host[i] = tot; count_host[i] = n;
+    }
+    return GLIC_OK;
+}
 
 size_t glic_geom_bytes(int P) { size_t b = 0; GeomState::carve(nullptr, P > 0 ? P : 0, &b); return b; }
 size_t glic_image_bytes(int width, int height) { size_t b = 0; ImageState::carve(nullptr, width, height, &b); return b; }
@@ -79,8 +120,9 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     cudaStream_t s = (cudaStream_t)stream;
     GeomState g = GeomState::carve(geom_ws, P);
     const ViewParams vp = make_view_params(view);
+    { StageTimer _t(GLIC_STAGE_PREPROCESS, s);
     if (int e = launch_preprocess_forward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, opacities, dc, sh, vp,
-                                          no_color != 0, radii, g, s)) return e;
+                                          no_color != 0, radii, g, s)) return e; }
     unsigned int total = 0;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&total, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     GLIC_CUDA_TRY(cudaStreamSynchronize(s));
@@ -114,15 +156,15 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
 
     int cur = 0;
     if (R > 0) {
-        if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], s)) return e;
+        { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], s)) return e; }
         const int bit = (int)higher_msb((uint32_t)T);                       // rasterizer_impl.cu:417
-        cur = launch_sort_pairs(R, 32 + bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s);
+        { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs(R, 32 + bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
         if (cur < 0) return cur;
     }
     const unsigned int flag = (unsigned int)cur;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
-    if (int e = launch_tile_ranges(R, bin.keys[cur], T, img, !no_color, s)) return e;
-    if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e;
+    { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, bin.keys[cur], T, img, !no_color, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_RENDER_FWD, s); if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
     if (num_buckets_host) {
         unsigned int nb = 0;
         GLIC_CUDA_TRY(cudaMemcpyAsync(&nb, &img.hdr->num_buckets, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -153,10 +195,11 @@ int glic_backward(int P, int sh_degree, int M, const float* means3D, const float
     GeomState g = GeomState::carve(const_cast<void*>(geom_ws), P);
     ImageState img = ImageState::carve(const_cast<void*>(image_ws), vp.W, vp.H);
     // 2-D gradient accumulators are filled by atomics: zero them here (11 floats / Gaussian)
+    { StageTimer _t(GLIC_STAGE_ZERO, s);
     GLIC_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, s));
     GLIC_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 4 * (size_t)P, s));
     GLIC_CUDA_TRY(cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)P, s));
-    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, s)); }
     if (R > 0) {
         BinningState bin = BinningState::carve(const_cast<void*>(binning_ws), R);
         const int64_t max_buckets = glic_max_buckets(R, vp.W, vp.H);
@@ -165,9 +208,11 @@ int glic_backward(int P, int sh_degree, int M, const float* means3D, const float
         const int T = vp.grid_x * vp.grid_y;
         const int passes = (32 + (int)higher_msb((uint32_t)T) + 7) / 8;
         const int cur = passes & 1;
+        StageTimer _t(GLIC_STAGE_RENDER_BWD, s);
         if (int e = launch_render_backward(P, vp, max_buckets, bin.vals[cur], g, img, smp, dL_dpix, dL_dmeans2D, dL_dconic,
                                            dL_dopacity, dL_dcolors, s)) return e;
     }
+    StageTimer _t(GLIC_STAGE_PREPROCESS_BWD, s);
     return launch_preprocess_backward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, sh, vp, radii, g,
                                       lambda_erank, dL_dmeans2D, dL_dconic, dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_ddc,
                                       dL_dsh, dL_dscales, dL_drotations, s);

@@ -45,6 +45,15 @@ extern unsigned long long g_launches;
         }                                                                                     \
     } while (0)
 
+// ---- optional per-stage cudaEvent timing (glic_profile_*) ---------------------------------
+bool profiling_on();
+void profile_mark(int stage, bool begin, cudaStream_t s);
+struct StageTimer {
+    int stage; cudaStream_t s; bool on;
+    StageTimer(int st, cudaStream_t stream) : stage(st), s(stream), on(profiling_on()) { if (on) profile_mark(stage, true, s); }
+    ~StageTimer() { if (on) profile_mark(stage, false, s); }
+};
+
 // ---- arena carving (128-byte aligned sub-arrays) ----------------------------------------
 struct Carver {
     char* base;

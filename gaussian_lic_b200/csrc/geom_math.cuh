@@ -39,19 +39,19 @@ struct Cov3 {
 GLIC_DI void cov3d_from_scale_rot(float sx, float sy, float sz, float mod, float4 q, Cov3& o) {
     sx = fmul(mod, sx); sy = fmul(mod, sy); sz = fmul(mod, sz);
     const float r = q.x, x = q.y, y = q.z, z = q.w;
+    // products kept as separate roundings: yy, zz, xz, rx, rz; xy, ry, yz are fused into the sums
+    // (this is what ptxas emits for the reference: SASS of preprocessCUDA)
     const float yy = fmul(y, y), zz = fmul(z, z);
+    const float xz = fmul(x, z), rx = fmul(r, x), rz = fmul(r, z);
     float t;
     t = fadd(yy, zz);               o.R[0] = fsub(1.0f, fadd(t, t));
-    const float xy = fmul(x, y), rz = fmul(r, z);
-    t = fsub(xy, rz);               o.R[1] = fadd(t, t);
-    const float xz = fmul(x, z), ry = fmul(r, y);
-    t = fadd(ry, xz);               o.R[2] = fadd(t, t);
-    t = fadd(xy, rz);               o.R[3] = fadd(t, t);
+    t = ffma(x, y, -rz);            o.R[1] = fadd(t, t);
+    t = ffma(r, y, xz);             o.R[2] = fadd(t, t);
+    t = ffma(x, y, rz);             o.R[3] = fadd(t, t);
     t = ffma(x, x, zz);             o.R[4] = fsub(1.0f, fadd(t, t));
-    const float yz = fmul(y, z), rx = fmul(r, x);
-    t = fsub(yz, rx);               o.R[5] = fadd(t, t);
-    t = fsub(xz, ry);               o.R[6] = fadd(t, t);
-    t = fadd(rx, yz);               o.R[7] = fadd(t, t);
+    t = ffma(y, z, -rx);            o.R[5] = fadd(t, t);
+    t = ffma(-r, y, xz);            o.R[6] = fadd(t, t);
+    t = ffma(y, z, rx);             o.R[7] = fadd(t, t);
     t = ffma(x, x, yy);             o.R[8] = fsub(1.0f, fadd(t, t));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {

@@ -102,7 +102,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         const float hw = xform_row(s_proj, 3, px, py, pz);
         const float pw = __frcp_rn(fadd(hw, 0.0000001f));
         const float ndcx = fmul(hx, pw), ndcy = fmul(hy, pw);
-        const float det = fsub(fmul(c2.a, c2.c), fmul(c2.b, c2.b));
+        const float det = ffma(c2.a, c2.c, -fmul(c2.b, c2.b));        // a*c - b*b as fma(a, c, -(b*b))
         if (det == 0.0f) active = false;
         const float det_inv = __frcp_rn(det);
         const float cox = fmul(c2.c, det_inv), coy = fmul(det_inv, -c2.b), coz = fmul(c2.a, det_inv);
@@ -110,7 +110,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         if (o < (1.0f / 255.0f)) active = false;                     // forward.h:30, forward.cu:293
         if (active) {
             const float mid = fmul(fadd(c2.a, c2.c), 0.5f);
-            const float lambda1 = fadd(mid, __fsqrt_rn(fmaxf(fsub(fmul(mid, mid), det), 0.1f)));
+            const float lambda1 = fadd(mid, __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f)));
             const float frad = ceilf(fmul(__fsqrt_rn(lambda1), 3.0f));
             const float mx = ndc_to_pix(ndcx, vp.W), my = ndc_to_pix(ndcy, vp.H);
             const int irad = (int)frad;

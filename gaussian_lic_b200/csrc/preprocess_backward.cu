@@ -109,8 +109,11 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
         dmz += (pr[8] * m_w - pr[11] * mul1) * g2x + (pr[9] * m_w - pr[11] * mul2) * g2y;
     }
 
-    // ---- SH backward (backward.cu:27-136) -------------------------------------------------------
-    {
+    // ---- SH backward (backward.cu:27-136).  Like the reference (`if (shs)`, backward.cu:352) the whole colour
+    // backward -- dL/ddc included -- is skipped when no SH-rest tensor is bound (M == 0). -------------------------
+    if (sh == nullptr) {
+        dL_ddc[3 * idx] = 0.f; dL_ddc[3 * idx + 1] = 0.f; dL_ddc[3 * idx + 2] = 0.f;
+    } else {
         const float ox = px - s_cam[0], oy = py - s_cam[1], oz = pz - s_cam[2];
         const float sum2 = ox * ox + oy * oy + oz * oz;
         const float inv = 1.0f / sqrtf(sum2);

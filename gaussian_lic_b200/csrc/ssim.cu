@@ -214,9 +214,11 @@ extern "C" int glic_l1_ssim_loss(int CH, int H, int W, float lambda_dssim, const
     cudaStream_t s = (cudaStream_t)stream;
     GLIC_CUDA_TRY(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
     dim3 grid((W + SB - 1) / SB, (H + SB - 1) / SB, CH), block(SB, SB);
-    ssim_forward_kernel<true><<<grid, block, 0, s>>>(H, W, C1, C2, img, gt, nullptr, d1, d2, d3, lambda_dssim, inv_n, loss_out);
+    { StageTimer _t(GLIC_STAGE_LOSS_FWD, s);
+    ssim_forward_kernel<true><<<grid, block, 0, s>>>(H, W, C1, C2, img, gt, nullptr, d1, d2, d3, lambda_dssim, inv_n, loss_out); }
     GLIC_LAUNCH_CHECK();
     if (dL_dimg) {
+        StageTimer _t(GLIC_STAGE_LOSS_BWD, s);
         ssim_backward_kernel<true><<<grid, block, 0, s>>>(H, W, img, gt, nullptr, d1, d2, d3, dL_dimg, -lambda_dssim * inv_n,
                                                           (1.0f - lambda_dssim) * inv_n);
         GLIC_LAUNCH_CHECK();

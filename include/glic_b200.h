@@ -182,6 +182,20 @@ GLIC_API int glic_debug_binning(int64_t num_rendered, const void* binning_ws, ui
 GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint32_t* ranges, uint32_t* bucket_offsets,
                      uint32_t* n_contrib, uint32_t* max_contrib, int64_t* counters2_host /* {R,B}, HOST pointer */, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Stage timing (cudaEvent pairs recorded on the launching stream around each stage; off by
+ * default).  glic_profile_enable(1) starts recording and resets the accumulators;
+ * glic_profile_read() synchronises the recorded events and returns, per stage, the summed
+ * milliseconds and the number of recordings since the last enable.  Stage ids: GLIC_STAGE_*.
+ * ------------------------------------------------------------------------------------- */
+enum {
+    GLIC_STAGE_PREPROCESS = 0, GLIC_STAGE_EMIT = 1, GLIC_STAGE_SORT = 2, GLIC_STAGE_RANGES = 3,
+    GLIC_STAGE_RENDER_FWD = 4, GLIC_STAGE_LOSS_FWD = 5, GLIC_STAGE_LOSS_BWD = 6, GLIC_STAGE_RENDER_BWD = 7,
+    GLIC_STAGE_PREPROCESS_BWD = 8, GLIC_STAGE_ADAM = 9, GLIC_STAGE_ZERO = 10, GLIC_STAGE_COUNT = 11
+};
+GLIC_API int glic_profile_enable(int on);
+GLIC_API int glic_profile_read(float* ms_host /*[GLIC_STAGE_COUNT]*/, int* count_host /*[GLIC_STAGE_COUNT]*/);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 GLIC_API uint64_t glic_launch_count(void);
 

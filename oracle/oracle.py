@@ -119,7 +119,7 @@ class Oracle:
                  dL_drots=np.zeros((P, 4), self.dtype), dL_dconic=np.zeros((P, 4), self.dtype))
         self.lib.glic_oracle_backward(
             C.c_void_p(fwd["state"]), _ptr(a["means"]), _ptr(a["scales"]), self.real(fwd["scale_modifier"]),
-            _ptr(a["rots"]), _ptr(a["dc"]), _ptr(a["sh"]), _ptr(view), _ptr(proj), _ptr(campos), self.real(tfx),
+            _ptr(a["rots"]), _ptr(a["dc"]), _ptr(a["sh"]) if a["sh"].size else None, _ptr(view), _ptr(proj), _ptr(campos), self.real(tfx),
             self.real(tfy), _ptr(lims), _ptr(g), self.real(lambda_erank), _ptr(o["dL_dmeans2D"]),
             _ptr(o["dL_dcolors"]), _ptr(o["dL_dopacity"]), _ptr(o["dL_dmeans3D"]), _ptr(o["dL_dcov3D"]),
             _ptr(o["dL_ddc"]), _ptr(o["dL_dsh"]), _ptr(o["dL_dscales"]), _ptr(o["dL_drots"]), _ptr(o["dL_dconic"]))
