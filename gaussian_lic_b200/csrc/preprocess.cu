@@ -66,6 +66,80 @@ GLIC_DI uint32_t lookback_exclusive(unsigned long long* status, int block, uint3
     return exclusive;
 }
 
+
+// ---- warp-balanced walk over every (Gaussian, candidate tile) pair of a warp ------------------
+// The 32 Gaussians of a warp own rects of wildly different sizes (1 .. thousands of tiles).  Instead of
+// one thread looping over its own rect, the warp flattens all its pairs into one list and tests 32 of
+// them per iteration: iterations = ceil(sum n / 32) instead of max n.  Lane l of iteration `base` takes
+// flattened item g = base + l, finds its owner by a 5-step binary search over the inclusive prefix held
+// in the lanes (shuffles), fetches the owner's parameters with dynamic-source shuffles and runs the
+// exact tile test.  Owners count their accepted tiles from the ballot restricted to their lane segment.
+// EMIT: the item additionally writes key/value at offset(owner) + #accepted-before, i.e. row-major order
+// inside each Gaussian's slot range, exactly like a sequential walk.
+GLIC_DI uint32_t seg_mask(int s0, int s1) {   // bits [s0, s1), 0 <= s0 <= s1 <= 32
+    const uint32_t hi = s1 >= 32 ? 0xffffffffu : ((1u << s1) - 1u);
+    const uint32_t lo = s0 >= 32 ? 0xffffffffu : ((1u << s0) - 1u);
+    return hi & ~lo;
+}
+
+template <bool EMIT>
+GLIC_DI uint32_t warp_tile_walk(int n, float mx, float my, float cox, float coy, float coz, float thr, int x0, int y0, int rw,
+                                int grid_x, uint32_t dbits, uint32_t idx, uint32_t off, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ vals) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = (uint32_t)n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - (uint32_t)n;
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t my_count = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t g = base + lane;
+        const bool valid = g < total;
+        int lo = 0, hi = 31;                      // first lane j with incl_j > g
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const uint32_t v = __shfl_sync(FULL, incl, mid);
+            if (v > g) hi = mid; else lo = mid + 1;
+        }
+        const int owner = lo & 31;
+        const uint32_t o_excl = __shfl_sync(FULL, excl, owner);
+        const float o_mx = __shfl_sync(FULL, mx, owner), o_my = __shfl_sync(FULL, my, owner);
+        const float o_cx = __shfl_sync(FULL, cox, owner), o_cy = __shfl_sync(FULL, coy, owner), o_cz = __shfl_sync(FULL, coz, owner);
+        const float o_thr = __shfl_sync(FULL, thr, owner);
+        const int o_x0 = __shfl_sync(FULL, x0, owner), o_y0 = __shfl_sync(FULL, y0, owner);
+        const int o_rw = max(__shfl_sync(FULL, rw, owner), 1);
+        const int t = valid ? (int)(g - o_excl) : 0;
+        const int ty = t / o_rw + o_y0, tx = t % o_rw + o_x0;
+        const bool ok = valid && tile_max_power(o_cx, o_cy, o_cz, o_mx, o_my, tx, ty) <= o_thr;
+        const uint32_t acc = __ballot_sync(FULL, ok);
+        if (EMIT) {
+            const uint32_t o_n = __shfl_sync(FULL, (uint32_t)n, owner);
+            const uint32_t o_cnt = __shfl_sync(FULL, my_count, owner);
+            const uint32_t o_off = __shfl_sync(FULL, off, owner);
+            const uint32_t o_idx = __shfl_sync(FULL, idx, owner);
+            const uint32_t o_db = __shfl_sync(FULL, dbits, owner);
+            if (ok) {
+                const int s0 = (int)(max(o_excl, base) - base), s1 = (int)(min(o_excl + o_n, base + 32u) - base);
+                const uint32_t pos = o_off + o_cnt + __popc(acc & seg_mask(s0, s1) & lt);
+                keys[pos] = ((uint64_t)(uint32_t)(ty * grid_x + tx) << 32) | (uint64_t)o_db;
+                vals[pos] = o_idx;
+            }
+        }
+        if (n > 0 && incl > base && excl < base + 32u) {
+            const int s0 = (int)(max(excl, base) - base), s1 = (int)(min(incl, base + 32u) - base);
+            my_count += __popc(acc & seg_mask(s0, s1));
+        }
+    }
+    return my_count;
+}
+
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, const float* __restrict__ scales,
                           float mod, const float4* __restrict__ rots, const float* __restrict__ opac,
@@ -89,13 +163,17 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
     float blue = 0.f, depth = 0.f;
     unsigned clampbits = 0;
+    // ---- phase 1: geometry of my Gaussian (fixed-order arithmetic) ----------------------------------
+    float px = 0.f, py = 0.f, pz = 0.f, mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, o = 0.f, thr = 0.f, tz = 0.f;
+    int irad = 0, n = 0, rx0 = 0, ry0 = 0, rw = 1;
     if (idx < P) {
-        const float px = means[3 * idx], py = means[3 * idx + 1], pz = means[3 * idx + 2];
+        px = means[3 * idx]; py = means[3 * idx + 1]; pz = means[3 * idx + 2];
         Cov3 c3;
         cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], mod, rots[idx], c3);
         Cov2 c2;
         cov2d_project(px, py, pz, s_view, vp.focal_x, vp.focal_y, vp.limx_neg, vp.limx_pos, vp.limy_neg, vp.limy_pos,
                       c3.c, c2);
+        tz = c2.tz;
         bool active = !(c2.tz <= 0.2f);                              // near cull, auxiliary.h:160
         const float hx = xform_row(s_proj, 0, px, py, pz);
         const float hy = xform_row(s_proj, 1, px, py, pz);
@@ -105,29 +183,30 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         const float det = ffma(c2.a, c2.c, -fmul(c2.b, c2.b));        // a*c - b*b as fma(a, c, -(b*b))
         if (det == 0.0f) active = false;
         const float det_inv = __frcp_rn(det);
-        const float cox = fmul(c2.c, det_inv), coy = fmul(det_inv, -c2.b), coz = fmul(c2.a, det_inv);
-        const float o = opac[idx];
+        cox = fmul(c2.c, det_inv); coy = fmul(det_inv, -c2.b); coz = fmul(c2.a, det_inv);
+        o = opac[idx];
         if (o < (1.0f / 255.0f)) active = false;                     // forward.h:30, forward.cu:293
         if (active) {
             const float mid = fmul(fadd(c2.a, c2.c), 0.5f);
             const float lambda1 = fadd(mid, __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f)));
             const float frad = ceilf(fmul(__fsqrt_rn(lambda1), 3.0f));
-            const float mx = ndc_to_pix(ndcx, vp.W), my = ndc_to_pix(ndcy, vp.H);
-            const int irad = (int)frad;
+            mx = ndc_to_pix(ndcx, vp.W); my = ndc_to_pix(ndcy, vp.H);
+            irad = (int)frad;
             const TileRect rc = tile_rect(mx, my, irad, vp.grid_x, vp.grid_y);
-            const float thr = logf(__fdiv_rn(o, 1.0f / 255.0f));     // forward.cu:302
-            const int rw = rc.x1 - rc.x0;
-            const int n = (rc.y1 - rc.y0) * rw;
-            uint32_t cnt = 0;
-            int tx = rc.x0, ty = rc.y0;
-            for (int t = 0; t < n; ++t) {                            // row-major walk over the rect
-                cnt += tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr;
-                if (++tx == rc.x1) { tx = rc.x0; ++ty; }
-            }
-            if (cnt > 0) {
+            thr = logf(__fdiv_rn(o, 1.0f / 255.0f));                 // forward.cu:302
+            rw = rc.x1 - rc.x0; rx0 = rc.x0; ry0 = rc.y0;
+            n = (rc.y1 - rc.y0) * rw;
+        }
+    }
+    // ---- phase 2: exact tile counting, balanced across the warp -------------------------------------------
+    const uint32_t cnt = warp_tile_walk<false>(n, mx, my, cox, coy, coz, thr, rx0, ry0, rw, vp.grid_x, 0u, 0u, 0u, nullptr, nullptr);
+    // ---- phase 3: colour of the survivors -----------------------------------------------------------------
+    if (cnt > 0) {
+        {
+            {
                 tiles = cnt;
                 radius = irad;
-                depth = c2.tz;
+                depth = tz;
                 float red = 0.f, green = 0.f;
                 if (!no_color) {
                     // SH -> RGB (forward.cu:29-77); tolerance-pinned, natural arithmetic.
@@ -224,29 +303,25 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
 __global__ void __launch_bounds__(256)
 emit_keys_kernel(int P, ViewParams vp, GeomState g, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const float4 r2 = g.rec[3 * idx + 2];
-    const uint32_t tiles = __float_as_uint(r2.w);
-    if (tiles == 0) return;
-    const float4 r0 = g.rec[3 * idx + 0];
-    const float4 r1 = g.rec[3 * idx + 1];
-    const uint32_t end = g.offsets[idx];
-    uint32_t off = end - tiles;
-    const float mx = r0.x, my = r0.y, cox = r0.z, coy = r0.w, coz = r1.x, o = r1.y;
-    const TileRect rc = tile_rect(mx, my, __float_as_int(r2.z), vp.grid_x, vp.grid_y);
-    const float thr = logf(__fdiv_rn(o, 1.0f / 255.0f));
-    const int rw = rc.x1 - rc.x0;
-    const int n = (rc.y1 - rc.y0) * rw;
-    const uint64_t dbits = __float_as_uint(r2.y);
-    int tx = rc.x0, ty = rc.y0;
-    for (int t = 0; t < n && off < end; ++t) {
-        if (tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr) {
-            keys[off] = ((uint64_t)(uint32_t)(ty * vp.grid_x + tx) << 32) | dbits;
-            vals[off] = (uint32_t)idx;
-            ++off;
+    int n = 0, x0 = 0, y0 = 0, rw = 1;
+    float mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, thr = 0.f;
+    uint32_t dbits = 0, off = 0;
+    if (idx < P) {
+        const float4 r2 = g.rec[3 * idx + 2];
+        const uint32_t tiles = __float_as_uint(r2.w);
+        if (tiles != 0) {
+            const float4 r0 = g.rec[3 * idx + 0];
+            const float4 r1 = g.rec[3 * idx + 1];
+            off = g.offsets[idx] - tiles;
+            mx = r0.x; my = r0.y; cox = r0.z; coy = r0.w; coz = r1.x;
+            const TileRect rc = tile_rect(mx, my, __float_as_int(r2.z), vp.grid_x, vp.grid_y);
+            thr = logf(__fdiv_rn(r1.y, 1.0f / 255.0f));
+            rw = rc.x1 - rc.x0; x0 = rc.x0; y0 = rc.y0;
+            n = (rc.y1 - rc.y0) * rw;
+            dbits = __float_as_uint(r2.y);
         }
-        if (++tx == rc.x1) { tx = rc.x0; ++ty; }
     }
+    warp_tile_walk<true>(n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, dbits, (uint32_t)idx, off, keys, vals);
 }
 
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
