@@ -52,9 +52,16 @@ __global__ void debug_geom_kernel(int P, GeomState g, float* depth, float* xy, f
     if (xy) { xy[2 * i] = r0.x; xy[2 * i + 1] = r0.y; }
     if (conic_opacity) { conic_opacity[4 * i] = r0.z; conic_opacity[4 * i + 1] = r0.w; conic_opacity[4 * i + 2] = r1.x; conic_opacity[4 * i + 3] = r1.y; }
     if (rgb) { rgb[3 * i] = r1.z; rgb[3 * i + 1] = r1.w; rgb[3 * i + 2] = r2.x; }
-    if (tiles) tiles[i] = __float_as_uint(r2.w);
+    if (tiles) tiles[i] = g.tiles[i];
     if (offsets) offsets[i] = g.offsets[i];
     if (clamped) { const unsigned c = g.clamped[i]; clamped[3 * i] = c & 1u; clamped[3 * i + 1] = (c >> 1) & 1u; clamped[3 * i + 2] = (c >> 2) & 1u; }
+}
+
+__global__ void debug_keys_kernel(long long R, GeomState g, const uint32_t* tile_keys, const uint32_t* point_list, uint64_t* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t gid = point_list[i];
+    out[i] = ((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(g.rec[3 * (size_t)gid + 2].y);
 }
 
 }  // namespace glic
@@ -123,6 +130,12 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     { StageTimer _t(GLIC_STAGE_PREPROCESS, s);
     if (int e = launch_preprocess_forward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, opacities, dc, sh, vp,
                                           no_color != 0, radii, g, s)) return e; }
+    {   // depth-first binning: order the Gaussians by (depth, index) once, then prefix-sum their tile counts in that order
+        StageTimer _t(GLIC_STAGE_SORT, s);
+        const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
+        if (cur < 0) return cur;
+        if (int e = launch_depth_scan(P, g, g.order[cur], s)) return e;
+    }
     unsigned int total = 0;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&total, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     GLIC_CUDA_TRY(cudaStreamSynchronize(s));
@@ -158,7 +171,8 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
     if (R > 0) {
         { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], s)) return e; }
         const int bit = (int)higher_msb((uint32_t)T);                       // rasterizer_impl.cu:417
-        { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs(R, 32 + bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
+        // pairs arrive ordered by (depth, index): a stable sort on the tile bits alone finishes the job
+        { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs32(R, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
         if (cur < 0) return cur;
     }
     const unsigned int flag = (unsigned int)cur;
@@ -206,7 +220,7 @@ int glic_backward(int P, int sh_degree, int M, const float* means3D, const float
         SampleState smp = SampleState::carve(const_cast<void*>(sample_ws), max_buckets);
         // the sort's ping-pong parity is a pure function of the pass count
         const int T = vp.grid_x * vp.grid_y;
-        const int passes = (32 + (int)higher_msb((uint32_t)T) + 7) / 8;
+        const int passes = ((int)higher_msb((uint32_t)T) + 7) / 8;
         const int cur = passes & 1;
         StageTimer _t(GLIC_STAGE_RENDER_BWD, s);
         if (int e = launch_render_backward(P, vp, max_buckets, bin.vals[cur], g, img, smp, dL_dpix, dL_dmeans2D, dL_dconic,
@@ -244,17 +258,22 @@ int glic_debug_geom(int P, const void* geom_ws, float* depth, float* xy, float* 
     return GLIC_OK;
 }
 
-int glic_debug_binning(int64_t R, const void* binning_ws, uint32_t* point_list, uint64_t* keys_sorted, void* stream) {
+int glic_debug_binning(int P, const void* geom_ws, int64_t R, const void* binning_ws, uint32_t* point_list, uint64_t* keys_sorted,
+                       void* stream) {
     if (R <= 0) return GLIC_OK;
-    if (!binning_ws) { set_error("debug_binning: null workspace"); return GLIC_ERR_WORKSPACE; }
+    if (!binning_ws || !geom_ws) { set_error("debug_binning: null workspace"); return GLIC_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     BinningState bin = BinningState::carve(const_cast<void*>(binning_ws), R);
+    GeomState g = GeomState::carve(const_cast<void*>(geom_ws), P);
     unsigned int cur = 0;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&cur, &bin.hdr->sorted_in_b, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     GLIC_CUDA_TRY(cudaStreamSynchronize(s));
     cur &= 1u;
     if (point_list) GLIC_CUDA_TRY(cudaMemcpyAsync(point_list, bin.vals[cur], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
-    if (keys_sorted) GLIC_CUDA_TRY(cudaMemcpyAsync(keys_sorted, bin.keys[cur], sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    if (keys_sorted) {   // the 64-bit (tile|depth) key of the reference, rebuilt from the tile key and the record's depth
+        debug_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((long long)R, g, bin.keys[cur], bin.vals[cur], keys_sorted);
+        GLIC_LAUNCH_CHECK();
+    }
     return GLIC_OK;
 }
 

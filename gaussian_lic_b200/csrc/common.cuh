@@ -1,11 +1,12 @@
 // common.cuh -- shared declarations of the glic_b200 CUDA library (sm_100a only).
 //
 // Workspace layouts (all opaque to callers; see DESIGN.md "HBM layout"):
-//   geom_ws   : GeomHeader | rec[3P] float4 (48 B AoS splat record) | offsets[P] u32 (inclusive
-//               scan of tiles_touched) | clamped[P] u8 | look-back status u64[blocks]
+//   geom_ws   : GeomHeader | rec[3P] float4 (48 B AoS splat record) | depth_keys[2][P] u32 + order[2][P] u32
+//               (depth sort ping-pong) | offsets[P] u32 (inclusive scan of tiles_touched in DEPTH order) |
+//               clamped[P] u8 | look-back status u64[blocks] | depth-sort temp
 //   image_ws  : ImageHeader | ranges[T] uint2 | bucket_offsets[T] u32 | max_contrib[T] u32 |
 //               n_contrib[HW] u32 | pixel_colors[3HW] f32
-//   binning_ws: BinHeader | keys[2][R] u64 | vals[2][R] u32 | sort temp
+//   binning_ws: BinHeader | tile keys[2][R] u32 | vals[2][R] u32 | sort temp
 //   sample_ws : bucket_to_tile[Bmax] u32 | ckpt[Bmax*256] float4 (T, C.r, C.g, C.b)
 #pragma once
 #include <cuda_runtime.h>
@@ -73,26 +74,42 @@ struct Carver {
 //   r0 = (x, y, conic.x, conic.y)   r1 = (conic.z, opacity, red, green)
 //   r2 = (blue, depth, radius as int bits, tiles_touched as uint bits)
 struct GeomHeader {
-    unsigned int ticket;        // dynamic CTA id for the fused scan
+    unsigned int ticket;        // dynamic CTA id of the emit kernel's fused scan
     unsigned int total;         // R = sum of tiles_touched
     unsigned int visible;       // #Gaussians with radius > 0
-    unsigned int pad[29];
+    unsigned int order_cur;     // which ping-pong half holds the depth-sorted order
+    unsigned int pad[28];
 };
+
+size_t sort_temp_bytes(int64_t n);
 
 struct GeomState {
     GeomHeader* hdr;
     float4* rec;
-    uint32_t* offsets;
+    uint32_t* depth_keys[2];    // float bits of depth (0xFFFFFFFF for culled Gaussians), sort ping-pong
+    uint32_t* order[2];         // Gaussian indices, sorted by (depth, index) after the depth sort
+    uint32_t* tiles;            // tiles_touched per Gaussian (index order)
+    uint32_t* offsets;          // per Gaussian: END of its slot range = inclusive scan of tiles over the depth order
     uint8_t* clamped;
     unsigned long long* scan_status;
+    void* sort_temp;
+    size_t sort_temp_size;
     __host__ static GeomState carve(void* ws, int P, size_t* bytes = nullptr) {
+        const size_t n = P > 0 ? size_t(P) : 1;
         Carver c(ws);
         GeomState g;
         g.hdr = c.take<GeomHeader>(1);
-        g.rec = c.take<float4>(size_t(3) * P);
-        g.offsets = c.take<uint32_t>(P);
-        g.clamped = c.take<uint8_t>(P);
-        g.scan_status = c.take<unsigned long long>((P + PRE_THREADS - 1) / PRE_THREADS + 1);
+        g.rec = c.take<float4>(size_t(3) * n);
+        g.depth_keys[0] = c.take<uint32_t>(n);
+        g.depth_keys[1] = c.take<uint32_t>(n);
+        g.order[0] = c.take<uint32_t>(n);
+        g.order[1] = c.take<uint32_t>(n);
+        g.tiles = c.take<uint32_t>(n);
+        g.offsets = c.take<uint32_t>(n);
+        g.clamped = c.take<uint8_t>(n);
+        g.scan_status = c.take<unsigned long long>((n + PRE_THREADS - 1) / PRE_THREADS + 1);
+        g.sort_temp_size = sort_temp_bytes((int64_t)n);
+        g.sort_temp = c.take<char>(g.sort_temp_size);
         if (bytes) *bytes = c.total();
         return g;
     }
@@ -132,11 +149,9 @@ struct BinHeader {
     unsigned int pad[31];
 };
 
-size_t sort_temp_bytes(int64_t n);
-
 struct BinningState {
     BinHeader* hdr;
-    uint64_t* keys[2];
+    uint32_t* keys[2];          // tile ids
     uint32_t* vals[2];
     void* sort_temp;
     size_t sort_temp_size;
@@ -145,8 +160,8 @@ struct BinningState {
         Carver c(ws);
         BinningState b;
         b.hdr = c.take<BinHeader>(1);
-        b.keys[0] = c.take<uint64_t>(n);
-        b.keys[1] = c.take<uint64_t>(n);
+        b.keys[0] = c.take<uint32_t>(n);
+        b.keys[1] = c.take<uint32_t>(n);
         b.vals[0] = c.take<uint32_t>(n);
         b.vals[1] = c.take<uint32_t>(n);
         b.sort_temp_size = sort_temp_bytes(R);
@@ -207,11 +222,14 @@ inline ViewParams make_view_params(const glic_view* v) {
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
                               const float* rots, const float* opac, const float* dc, const float* sh,
                               const ViewParams& vp, bool no_color, int* radii, GeomState g, cudaStream_t s);
-int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint64_t* keys, uint32_t* vals, cudaStream_t s);
+int launch_depth_scan(int P, GeomState g, const uint32_t* order, cudaStream_t s);
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
 // Sorts on bits [0,end_bit); returns 0/1 = index of the ping-pong buffer holding the result, <0 on error.
 int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
                       cudaStream_t s);
-int launch_tile_ranges(int64_t R, const uint64_t* keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s);
+int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                        cudaStream_t s);
+int launch_tile_ranges(int64_t R, const uint32_t* tile_keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s);
 int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* point_list, GeomState g, ImageState img,
                           SampleState smp, float* out_color, float* out_final_T, cudaStream_t s);
 int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,

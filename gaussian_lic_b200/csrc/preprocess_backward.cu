@@ -7,6 +7,7 @@
 // Gaussians).  Forward intermediates (cov3D, T) are recomputed from scale/rotation instead of
 // being stored (24 B/Gaussian less state, and the inputs are read anyway).
 #include "geom_math.cuh"
+#include "warp_rows.cuh"
 
 namespace glic {
 
@@ -18,7 +19,9 @@ __device__ __constant__ float bSH_C3[7] = {-0.5900435899266435f, 2.8906114426405
                                            -0.5900435899266435f};
 constexpr float bSH_C0 = 0.28209479177387814f;
 
-__global__ void __launch_bounds__(256)
+constexpr int PB_THREADS = 128;
+
+__global__ void __launch_bounds__(PB_THREADS)
 preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means, const float* __restrict__ scales,
                            float mod, const float4* __restrict__ rots, const float* __restrict__ sh, ViewParams vp,
                            const int* __restrict__ radii, const uint8_t* __restrict__ clamped, float lambda_erank,
@@ -27,23 +30,33 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
                            float* __restrict__ dL_dcov3D, float* __restrict__ dL_ddc, float* __restrict__ dL_dsh,
                            float* __restrict__ dL_dscales, float4* __restrict__ dL_drots) {
     __shared__ float s_view[16], s_proj[16], s_cam[3];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) float s_sh[PB_THREADS / 32][32 * SH_ROW_MAX];    // SH rows in, dL/dSH rows out
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) s_view[tid] = vp.view[tid];
     else if (tid < 32) s_proj[tid - 16] = vp.proj[tid - 16];
     else if (tid < 35) s_cam[tid - 32] = vp.campos[tid - 32];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + tid;
-    if (idx >= P) return;
-    float* dsh = dL_dsh + (size_t)idx * M * 3;
-    if (!(radii[idx] > 0)) {
+    const int K = 3 * M;
+    const bool staged = K > 0 && K <= SH_ROW_MAX && sh != nullptr;
+    const int wfirst = blockIdx.x * blockDim.x + warp * 32;
+    const int wcnt = min(32, P - wfirst);
+    if (wcnt <= 0) return;                                         // whole warp beyond P (warp-uniform)
+    float* slab = s_sh[warp];
+    if (staged && D > 0) warp_load_rows(sh, (size_t)wfirst, wcnt, K, slab, lane);
+    // dL/dSH row of this thread: shared-memory slab (written back coalesced below) or global memory
+    float* dsh = staged ? (slab + lane * K) : (dL_dsh + (size_t)(idx < P ? idx : 0) * K);
+    const bool visible = idx < P && radii[idx] > 0;
+    if (!visible) {
+        if (idx < P) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { dL_dmeans3D[3 * idx + k] = 0.f; dL_ddc[3 * idx + k] = 0.f; dL_dscales[3 * idx + k] = 0.f; }
+            for (int k = 0; k < 3; ++k) { dL_dmeans3D[3 * idx + k] = 0.f; dL_ddc[3 * idx + k] = 0.f; dL_dscales[3 * idx + k] = 0.f; }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = 0.f;
-        dL_drots[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < 3 * M; ++k) dsh[k] = 0.f;
-        return;
-    }
+            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = 0.f;
+            dL_drots[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (idx < P || staged) for (int k = 0; k < K; ++k) dsh[k] = 0.f;
+    } else {
     const float px = means[3 * idx], py = means[3 * idx + 1], pz = means[3 * idx + 2];
     const float s0 = scales[3 * idx], s1 = scales[3 * idx + 1], s2 = scales[3 * idx + 2];
     const float4 q = rots[idx];
@@ -126,7 +139,15 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
         for (int ch = 0; ch < 3; ++ch) dL_ddc[3 * idx + ch] = bSH_C0 * dRGB[ch];
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/d(dir)
         if (D > 0) {
-            const float* s = sh + (size_t)idx * M * 3;
+            float sv[SH_ROW_MAX];                                  // input row -> registers (the slab row is reused for the output)
+            if (staged) {
+#pragma unroll
+                for (int k = 0; k < SH_ROW_MAX; ++k) sv[k] = k < K ? slab[lane * K + k] : 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < SH_ROW_MAX; ++k) sv[k] = k < K ? sh[(size_t)idx * K + k] : 0.f;
+            }
+            const float* s = sv;   // rows are lane-private: no cross-lane hazard between this read and the dsh writes
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             float bs[15];
             bs[0] = -bSH_C1 * y; bs[1] = bSH_C1 * z; bs[2] = -bSH_C1 * x;
@@ -232,6 +253,8 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
         dL_dscales[3 * idx] = ds[0]; dL_dscales[3 * idx + 1] = ds[1]; dL_dscales[3 * idx + 2] = ds[2];
         dL_drots[idx] = dq;
     }
+    }   // visible
+    if (staged) warp_store_rows(dL_dsh, (size_t)wfirst, wcnt, K, slab, lane);
 }
 
 int launch_preprocess_backward(int P, int D, int M, const float* means, const float* scales, float mod,
@@ -239,7 +262,7 @@ int launch_preprocess_backward(int P, int D, int M, const float* means, const fl
                                float lambda_erank, const float* dL_dmean2D, const float* dL_dconic,
                                const float* dL_dcolors, float* dL_dmeans3D, float* dL_dcov3D, float* dL_ddc,
                                float* dL_dsh, float* dL_dscales, float* dL_drots, cudaStream_t s) {
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, s>>>(
+    preprocess_backward_kernel<<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
         P, D, M, means, scales, mod, reinterpret_cast<const float4*>(rots), sh, vp, radii, g.clamped, lambda_erank,
         dL_dmean2D, dL_dconic, dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh, dL_dscales,
         reinterpret_cast<float4*>(dL_drots));

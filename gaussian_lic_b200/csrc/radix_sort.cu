@@ -8,8 +8,8 @@
 //   1. one histogram kernel builds the global digit histogram of EVERY pass in a single read of
 //      the keys (8 B/pair);
 //   2. a tiny kernel turns each histogram into exclusive digit offsets;
-//   3. one kernel per pass: each CTA ranks a 4096-pair tile (warp-synchronous match-any ranking,
-//      stable), resolves its global digit offsets with a per-digit decoupled look-back chain over
+//   3. one kernel per pass: each CTA ranks a 4096-pair tile (warp-synchronous ranking, stable: MATCH.ANY for
+//      64-bit keys, a ballot cascade for 32-bit keys whose digits repeat heavily inside a warp), resolves its global digit offsets with a per-digit decoupled look-back chain over
 //      dynamically ordered CTAs (no second read of the data), stages the tile in shared memory in
 //      sorted order and writes digit runs out coalesced (24 B/pair/pass).
 // Algorithmic HBM traffic: (8 + 24*passes) B per pair (152 B @ 45 bits).
@@ -59,14 +59,15 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 }
 
 // ---- 1. all-pass histogram --------------------------------------------------------------
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-sort_histogram_kernel(const uint64_t* __restrict__ keys, int64_t n, int passes, int end_bit, uint32_t* __restrict__ hist) {
+sort_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int end_bit, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
+        const KeyT k = keys[i];
         for (int p = 0; p < passes; ++p) {
             const int shift = p * RADIX_BITS;
             const int bits = min(RADIX_BITS, end_bit - shift);
@@ -101,8 +102,9 @@ __global__ void __launch_bounds__(RADIX) sort_scan_hist_kernel(uint32_t* __restr
 }
 
 // ---- 3. one onesweep pass -------------------------------------------------------------------
+template <typename KeyT>
 struct __align__(16) PassSmem {
-    uint64_t keys[SORT_TILE];
+    KeyT keys[SORT_TILE];
     uint32_t vals[SORT_TILE];
     uint32_t warp_cnt[SORT_WARPS][RADIX];
     uint32_t digit_excl[RADIX];
@@ -111,12 +113,13 @@ struct __align__(16) PassSmem {
     uint32_t block_id;
 };
 
+template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                      const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
+    PassSmem<KeyT>& sm = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t dmask = (1u << bits) - 1u;
 
@@ -128,13 +131,13 @@ onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
     const int count = (int)min((int64_t)SORT_TILE, n - tile_base);
 
     // -- load (warp-striped: lane l, item j <-> element warp*512 + j*32 + l; order-preserving)
-    uint64_t k[SORT_ITEMS];
+    KeyT k[SORT_ITEMS];
     uint32_t rank[SORT_ITEMS];
     const int wbase = warp * (32 * SORT_ITEMS);
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; ++j) {
         const int li = wbase + j * 32 + lane;
-        k[j] = li < count ? keys_in[tile_base + li] : ~0ull;
+        k[j] = li < count ? keys_in[tile_base + li] : (KeyT)~(KeyT)0;
     }
     // -- stable rank inside the warp's digit streams
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -145,8 +148,19 @@ onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
         const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         uint32_t r = 0;
+        uint32_t bpeers = vmask;
+        if (sizeof(KeyT) == 4) {   // 32-bit keys: peers from `bits` ballots (cost independent of the digit distribution)
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                if (b < bits) {
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit && valid);
+                    bpeers &= bit ? bal : ~bal;
+                }
+            }
+        }
         if (valid) {
-            const uint32_t peers = __match_any_sync(vmask, d);
+            const uint32_t peers = sizeof(KeyT) == 4 ? bpeers : __match_any_sync(vmask, d);
             const int leader = __ffs(peers) - 1;
             uint32_t c = 0;
             if (lane == leader) {
@@ -226,7 +240,7 @@ onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
 
     // -- coalesced write-out of digit runs
     for (int i = tid; i < count; i += SORT_THREADS) {
-        const uint64_t key = sm.keys[i];
+        const KeyT key = sm.keys[i];
         const uint32_t d = (uint32_t)(key >> shift) & dmask;
         const size_t dst = (size_t)sm.global_base[d] + i;
         keys_out[dst] = key;
@@ -241,9 +255,10 @@ size_t sort_temp_bytes(int64_t n) {
     return sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)MAX_PASSES * blocks * RADIX) + 256;
 }
 
-int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                      cudaStream_t s) {
-    if (end_bit < 1 || end_bit > 64) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
+template <typename KeyT>
+static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                               cudaStream_t s) {
+    if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
     if (n >= (int64_t)VALUE_MASK) { set_error("sort: n too large"); return GLIC_ERR_INVALID_ARGUMENT; }
     if (n <= 0) return 0;
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
@@ -256,12 +271,12 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
 
     static bool attr_set = false;
     if (!attr_set) {
-        GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(PassSmem)));
+        GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PassSmem<KeyT>)));
         attr_set = true;
     }
     int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
-    sort_histogram_kernel<<<hist_blocks, 256, 0, s>>>(keys[0], n, passes, end_bit, t.hist);
+    sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, passes, end_bit, t.hist);
     GLIC_LAUNCH_CHECK();
     sort_scan_hist_kernel<<<passes, RADIX, 0, s>>>(t.hist);
     GLIC_LAUNCH_CHECK();
@@ -269,13 +284,23 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
     for (int p = 0; p < passes; ++p) {
         const int shift = p * RADIX_BITS;
         const int bits = min(RADIX_BITS, end_bit - shift);
-        onesweep_pass_kernel<<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem), s>>>(
+        onesweep_pass_kernel<KeyT><<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem<KeyT>), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, bits, t.hist + p * RADIX,
             t.status + (size_t)p * blocks * RADIX, t.tickets + p);
         GLIC_LAUNCH_CHECK();
         cur ^= 1;
     }
     return cur;
+}
+
+int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                      cudaStream_t s) {
+    return launch_sort_pairs_t<uint64_t>(n, end_bit, keys, vals, temp, temp_bytes, s);
+}
+
+int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                        cudaStream_t s) {
+    return launch_sort_pairs_t<uint32_t>(n, end_bit, keys, vals, temp, temp_bytes, s);
 }
 
 }  // namespace glic

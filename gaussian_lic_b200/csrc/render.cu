@@ -27,14 +27,14 @@ namespace glic {
 
 // ---- tile ranges -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys, uint32_t T, uint2* __restrict__ ranges) {
+tile_ranges_kernel(int64_t R, const uint32_t* __restrict__ keys, uint32_t T, uint2* __restrict__ ranges) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
-    const uint32_t cur = (uint32_t)(keys[i] >> 32);
+    const uint32_t cur = keys[i];
     if (cur >= T) return;
     if (i == 0) ranges[cur].x = 0;
     else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        const uint32_t prev = keys[i - 1];
         if (cur != prev) {
             if (prev < T) ranges[prev].y = (uint32_t)i;
             ranges[cur].x = (uint32_t)i;
@@ -334,7 +334,7 @@ render_backward_kernel(ViewParams vp, const ImageHeader* __restrict__ hdr, const
 }
 
 // ---- launchers ------------------------------------------------------------------------------
-int launch_tile_ranges(int64_t R, const uint64_t* keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s) {
+int launch_tile_ranges(int64_t R, const uint32_t* keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s) {
     GLIC_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, s));
     if (R > 0) {
         tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, keys_sorted, (uint32_t)T, img.ranges);

@@ -290,7 +290,7 @@ class CRasterizer:
         capi.check(lib.glic_debug_geom(P, capi.ptr(self.geom_ws), capi.ptr(d["depth"]), capi.ptr(d["xy"]),
                                        capi.ptr(d["conic_opacity"]), capi.ptr(d["rgb"]), capi.ptr(d["tiles_touched"]),
                                        capi.ptr(d["offsets"]), capi.ptr(d["clamped"]), None), "debug_geom")
-        capi.check(lib.glic_debug_binning(R, capi.ptr(self.binning_ws), capi.ptr(d["point_list"]),
+        capi.check(lib.glic_debug_binning(P, capi.ptr(self.geom_ws), R, capi.ptr(self.binning_ws), capi.ptr(d["point_list"]),
                                           capi.ptr(d["keys_sorted"]), None), "debug_binning")
         cnt = (C.c_int64 * 2)()
         capi.check(lib.glic_debug_image(W, H, capi.ptr(self.image_ws), capi.ptr(d["ranges"]),

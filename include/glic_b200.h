@@ -172,13 +172,14 @@ GLIC_API int glic_knn_mean_dist2(int P, const float* points, float* mean_dists, 
 /* ---------------------------------------------------------------------------------------
  * Introspection for parity tests (copies internal state to caller DEVICE buffers; any pointer
  * may be NULL).  Shapes: depth[P] xy[P,2] conic_opacity[P,4] rgb[P,3] tiles_touched[P]
- * offsets[P] clamped[P,3] (u8) | point_list[R] keys_sorted[R] | ranges[T,2] bucket_offsets[T]
+ * offsets[P] (end of each Gaussian's slot range in the depth-ordered key list) clamped[P,3] (u8) |
+ * point_list[R] keys_sorted[R] ((tile<<32)|depth bits, rebuilt) | ranges[T,2] bucket_offsets[T]
  * n_contrib[H*W] max_contrib[T].
  * ------------------------------------------------------------------------------------- */
 GLIC_API int glic_debug_geom(int P, const void* geom_ws, float* depth, float* xy, float* conic_opacity, float* rgb,
                     uint32_t* tiles_touched, uint32_t* offsets, uint8_t* clamped, void* stream);
-GLIC_API int glic_debug_binning(int64_t num_rendered, const void* binning_ws, uint32_t* point_list,
-                       uint64_t* keys_sorted, void* stream);
+GLIC_API int glic_debug_binning(int P, const void* geom_ws, int64_t num_rendered, const void* binning_ws,
+                                uint32_t* point_list, uint64_t* keys_sorted, void* stream);
 GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint32_t* ranges, uint32_t* bucket_offsets,
                      uint32_t* n_contrib, uint32_t* max_contrib, int64_t* counters2_host /* {R,B}, HOST pointer */, void* stream);
 
