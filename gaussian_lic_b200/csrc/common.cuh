@@ -118,7 +118,8 @@ struct GeomState {
 struct ImageHeader {
     long long num_rendered;     // R
     unsigned int num_buckets;   // B
-    unsigned int pad[29];
+    unsigned int num_live_buckets;   // buckets some pixel reached (backward work list)
+    unsigned int pad[28];
 };
 
 struct ImageState {
@@ -126,6 +127,7 @@ struct ImageState {
     uint2* ranges;
     uint32_t* bucket_offsets;
     uint32_t* max_contrib;
+    uint32_t* live_offsets;     // inclusive scan of ceil(max_contrib/32) (backward's live-bucket list)
     uint32_t* n_contrib;
     float* pixel_colors;
     __host__ static ImageState carve(void* ws, int W, int H, size_t* bytes = nullptr) {
@@ -137,6 +139,7 @@ struct ImageState {
         s.ranges = c.take<uint2>(T);
         s.bucket_offsets = c.take<uint32_t>(T);
         s.max_contrib = c.take<uint32_t>(T);
+        s.live_offsets = c.take<uint32_t>(T);
         s.n_contrib = c.take<uint32_t>(HW);
         s.pixel_colors = c.take<float>(3 * HW);
         if (bytes) *bytes = c.total();

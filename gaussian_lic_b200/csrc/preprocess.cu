@@ -155,15 +155,11 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
     }
     __syncthreads();
     const uint32_t n_chunks = w.n_chunks;
-    // -- chunks round-robin over the warps
+    // -- chunks round-robin over the warps.  A warp's chunk index only grows, so its slot is found by
+    //    advancing a cursor (warp-uniform; amortised O(1)) instead of searching the table every time.
+    int s = 0;
     for (uint32_t ch = warp; ch < n_chunks; ch += PRE_THREADS / 32) {
-        // slot of this chunk: last s with chunk_prefix[s] <= ch  (lane-parallel search over <= 256 entries)
-        uint32_t below = 0;
-        for (uint32_t b0 = 0; b0 < total_big; b0 += 32) {
-            const uint32_t s = b0 + lane;
-            below += __popc(__ballot_sync(FULL, s < total_big && w.chunk_prefix[s] <= ch));
-        }
-        const int s = (int)below - 1;
+        while (w.chunk_prefix[s + 1] <= ch) ++s;
         const int t = (int)(ch - w.chunk_prefix[s]) * 32 + lane;
         const int sn = w.n[s], srw = w.rw[s];
         const bool valid = t < sn;

@@ -22,6 +22,7 @@
 // fixed-order intrinsics of geom_math.cuh, so colours/transmittance agree bit-for-bit with the
 // reference build on the same sorted list.
 #include "geom_math.cuh"
+#include <algorithm>
 
 namespace glic {
 
@@ -203,133 +204,185 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
 }
 
 // ---- per-splat backward --------------------------------------------------------------------
+// Only buckets that some pixel actually reached are worth a warp: tile t has ceil(max_contrib[t]/32) LIVE
+// buckets (at cfg2: 19 k of 245 k).  live_scan_kernel prefix-sums them; the backward kernel is persistent
+// (a fixed number of CTAs, warps stride over the live list), so every resident warp does useful work and no
+// launch geometry depends on a device-side count.
+__global__ void __launch_bounds__(1024)
+live_scan_kernel(int T, const uint32_t* __restrict__ max_contrib, uint32_t* __restrict__ live_offsets, ImageHeader* hdr) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        const uint32_t v = t < T ? (max_contrib[t] + BUCKET - 1) / BUCKET : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_tot[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t out = carry + warp_tot[warp] + incl;
+        if (t < T) live_offsets[t] = out;
+        __syncthreads();
+        if (tid == 1023) carry = out;
+        __syncthreads();
+    }
+    if (tid == 0) hdr->num_live_buckets = carry;
+}
+
 constexpr int BWD_WARPS = 8;
 
 __global__ void __launch_bounds__(BWD_WARPS * 32)
-render_backward_kernel(ViewParams vp, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
+render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
-                       const uint32_t* __restrict__ bucket_offsets, const uint32_t* __restrict__ bucket_to_tile,
+                       const uint32_t* __restrict__ bucket_offsets, const uint32_t* __restrict__ live_offsets,
                        const float4* __restrict__ ckpt, const uint32_t* __restrict__ n_contrib,
-                       const uint32_t* __restrict__ max_contrib, const float* __restrict__ pixel_colors,
-                       const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
-                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolors) {
-    __shared__ float s_pix[BWD_WARPS][8][32];
+                       const float* __restrict__ pixel_colors, const float* __restrict__ dL_dpix,
+                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+                       float* __restrict__ dL_dcolors) {
+    // per warp: two 32-pixel groups (ring) of {T, C-Cfinal} state and {dL/dC, n_contrib} constants
+    __shared__ float4 s_state[BWD_WARPS][32];
+    __shared__ float4 s_const[BWD_WARPS][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bucket = blockIdx.x * BWD_WARPS + warp;
-    if (bucket >= hdr->num_buckets) return;                     // warp-uniform
-
-    const uint32_t tile = bucket_to_tile[bucket];
-    const uint2 range = ranges[tile];
-    const int n_splats = (int)(range.y - range.x);
-    const uint32_t bbm = tile == 0 ? 0u : bucket_offsets[tile - 1];
-    const int bucket_in_tile = (int)(bucket - bbm);
-    const int splat_in_tile = bucket_in_tile * BUCKET + lane;
-    const bool valid_splat = splat_in_tile < n_splats;
-    if ((uint32_t)(bucket_in_tile * BUCKET) >= max_contrib[tile]) return;   // nobody got this far
-
-    uint32_t gid = 0;
-    float mx = 0.f, my = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    if (valid_splat) {
-        gid = point_list[range.x + splat_in_tile];
-        const float4 r0 = rec[3 * (size_t)gid + 0];
-        const float4 r1 = rec[3 * (size_t)gid + 1];
-        const float4 r2 = rec[3 * (size_t)gid + 2];
-        mx = r0.x; my = r0.y; cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
-    }
-    const int tile_x = tile % vp.grid_x, tile_y = tile / vp.grid_x;
-    const int pix_min_x = tile_x * TILE, pix_min_y = tile_y * TILE;
+    const uint32_t n_live = hdr->num_live_buckets;
+    const uint32_t warps_total = gridDim.x * BWD_WARPS;
     const size_t HW = (size_t)vp.W * vp.H;
     const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
-    const float4* ck = ckpt + (size_t)bucket * TILE_PIX;
-    float (*sp)[32] = s_pix[warp];
+    float4* st = s_state[warp];
+    float4* cs = s_const[warp];
 
-    float acc_mx = 0.f, acc_my = 0.f, acc_cx = 0.f, acc_cy = 0.f, acc_cw = 0.f, acc_o = 0.f;
-    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
-    float T = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    int nc = 0;
+    for (uint32_t live = blockIdx.x * BWD_WARPS + warp; live < n_live; live += warps_total) {
+        // tile of this live bucket: first t with live_offsets[t] > live -- 32-ary search, one probe per lane
+        int lo = 0, cnt = T;
+        while (cnt > 1) {
+            const int step = (cnt + 31) >> 5;
+            const int probe = lo + min((lane + 1) * step, cnt) - 1;              // last tile of this lane's sub-range
+            const unsigned hit = __ballot_sync(0xffffffffu, live_offsets[probe] > live);
+            const int first = __ffs(hit) - 1;                                      // hit != 0: live < live_offsets[T-1]
+            lo += first * step;
+            cnt = min(step, cnt - first * step);
+        }
+        const uint32_t tile = (uint32_t)lo;
+        const int bucket_in_tile = (int)(live - (tile == 0 ? 0u : live_offsets[tile - 1]));
+        const uint32_t bucket = (tile == 0 ? 0u : bucket_offsets[tile - 1]) + (uint32_t)bucket_in_tile;
+        const uint2 range = ranges[tile];
+        const int n_splats = (int)(range.y - range.x);
+        const int splat_in_tile = bucket_in_tile * BUCKET + lane;
+        const bool valid_splat = splat_in_tile < n_splats;
 
-    for (int i = 0; i < TILE_PIX + 31; ++i) {
-        if ((i & 31) == 0 && i < TILE_PIX) {
-            // coalesced fill of the next 32 pixels' state: lane l <-> pixel i + l of the tile
-            __syncwarp();
-            const int p = i + lane;
-            const int qx = pix_min_x + (p & (TILE - 1)), qy = pix_min_y + (p >> 4);
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f;
-            int n = 0;
-            if (qx < vp.W && qy < vp.H) {
-                const size_t q = (size_t)qy * vp.W + qx;
-                n = (int)n_contrib[q];
-                if (n > bucket_in_tile * BUCKET) {               // pixel reached this bucket: checkpoint is valid
-                    const float4 k4 = ck[p];
-                    v0 = k4.x;
-                    v1 = k4.y - pixel_colors[q];
-                    v2 = k4.z - pixel_colors[HW + q];
-                    v3 = k4.w - pixel_colors[2 * HW + q];
-                    v4 = dL_dpix[q]; v5 = dL_dpix[HW + q]; v6 = dL_dpix[2 * HW + q];
-                } else {
-                    n = 0;
+        uint32_t gid = 0;
+        float mx = 0.f, my = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (valid_splat) {
+            gid = point_list[range.x + splat_in_tile];
+            const float4 r0 = rec[3 * (size_t)gid + 0];
+            const float4 r1 = rec[3 * (size_t)gid + 1];
+            const float4 r2 = rec[3 * (size_t)gid + 2];
+            mx = r0.x; my = r0.y; cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
+        }
+        const int tile_x = tile % vp.grid_x, tile_y = tile / vp.grid_x;
+        const int pix_min_x = tile_x * TILE, pix_min_y = tile_y * TILE;
+        const float4* ck = ckpt + (size_t)bucket * TILE_PIX;
+
+        float acc_mx = 0.f, acc_my = 0.f, acc_cx = 0.f, acc_cy = 0.f, acc_cw = 0.f, acc_o = 0.f;
+        float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
+        float T = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;
+        // pixel handled by this lane at step i is p = i - lane; track its coordinates incrementally
+        int p = -lane;
+        float pfx = (float)(pix_min_x + ((-lane) & (TILE - 1))), pfy = (float)(pix_min_y) - (float)((lane + TILE - 1) >> 4);
+        const float x_wrap = (float)(pix_min_x + TILE);
+
+        for (int i = 0; i < TILE_PIX + 31; ++i, ++p) {
+            if ((i & 31) == 0 && i < TILE_PIX) {
+                // coalesced fill of the next 32 pixels: lane l <-> pixel i + l of the tile
+                __syncwarp();
+                const int q = i + lane;
+                const int qx = pix_min_x + (q & (TILE - 1)), qy = pix_min_y + (q >> 4);
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qx < vp.W && qy < vp.H) {
+                    const size_t qi = (size_t)qy * vp.W + qx;
+                    const int n = (int)n_contrib[qi];
+                    if (n > bucket_in_tile * BUCKET) {               // pixel reached this bucket: checkpoint is valid
+                        const float4 k4 = ck[q];
+                        sv = make_float4(k4.x, k4.y - pixel_colors[qi], k4.z - pixel_colors[HW + qi], k4.w - pixel_colors[2 * HW + qi]);
+                        cv = make_float4(dL_dpix[qi], dL_dpix[HW + qi], dL_dpix[2 * HW + qi], __int_as_float(n));
+                    }
+                }
+                st[lane] = sv;
+                cs[(i & 32) + lane] = cv;
+                __syncwarp();
+            }
+            // hand the running state to the next splat (lane+1), which treats the same pixel next
+            T = __shfl_up_sync(0xffffffffu, T, 1);
+            ar0 = __shfl_up_sync(0xffffffffu, ar0, 1);
+            ar1 = __shfl_up_sync(0xffffffffu, ar1, 1);
+            ar2 = __shfl_up_sync(0xffffffffu, ar2, 1);
+            if (lane == 0 && i < TILE_PIX) {
+                const float4 sv = st[i & 31];
+                T = sv.x; ar0 = sv.y; ar1 = sv.z; ar2 = sv.w;
+            }
+            if (valid_splat && p >= 0 && p < TILE_PIX) {
+                const float4 cv = cs[p & 63];
+                if (splat_in_tile < __float_as_int(cv.w)) {
+                    const float dx = fsub(mx, pfx), dy = fsub(my, pfy);
+                    const float power = splat_power(dx, dy, cx, cy, cz);
+                    if (power <= 0.0f) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, fmul(op, G));
+                        if (alpha >= (1.0f / 255.0f)) {
+                            const float g0 = cv.x, g1 = cv.y, g2 = cv.z;
+                            const float one_m = fsub(1.0f, alpha);
+                            const float dchannel_dcolor = alpha * T;
+                            const float alpha_inverse = __fdividef(1.0f, one_m);   // MUFU.RCP (gradients are tolerance-pinned)
+                            float dL_dalpha;
+                            ar0 += dchannel_dcolor * c0; acc_c0 += dchannel_dcolor * g0; dL_dalpha = ((c0 * T) + alpha_inverse * ar0) * g0;
+                            ar1 += dchannel_dcolor * c1; acc_c1 += dchannel_dcolor * g1; dL_dalpha += ((c1 * T) + alpha_inverse * ar1) * g1;
+                            ar2 += dchannel_dcolor * c2; acc_c2 += dchannel_dcolor * g2; dL_dalpha += ((c2 * T) + alpha_inverse * ar2) * g2;
+                            T = fmul(T, one_m);
+                            const float dL_dG = op * dL_dalpha;
+                            const float gdx = G * dx, gdy = G * dy;
+                            const float dG_ddelx = -gdx * cx - gdy * cy;
+                            const float dG_ddely = -gdy * cz - gdx * cy;
+                            acc_mx += dL_dG * dG_ddelx * ddelx_dx;
+                            acc_my += dL_dG * dG_ddely * ddely_dy;
+                            acc_cx += -0.5f * gdx * dx * dL_dG;
+                            acc_cy += -0.5f * gdx * dy * dL_dG;
+                            acc_cw += -0.5f * gdy * dy * dL_dG;
+                            acc_o += G * dL_dalpha;
+                        }
+                    }
                 }
             }
-            sp[0][lane] = v0; sp[1][lane] = v1; sp[2][lane] = v2; sp[3][lane] = v3;
-            sp[4][lane] = v4; sp[5][lane] = v5; sp[6][lane] = v6; sp[7][lane] = __int_as_float(n);
-            __syncwarp();
+            // next pixel of this lane (row-major inside the 16x16 tile)
+            pfx += 1.0f;
+            if (pfx == x_wrap) { pfx -= (float)TILE; pfy += 1.0f; }
         }
-        // hand the running state to the next splat (lane+1), which treats the same pixel next
-        T = __shfl_up_sync(0xffffffffu, T, 1);
-        ar0 = __shfl_up_sync(0xffffffffu, ar0, 1);
-        ar1 = __shfl_up_sync(0xffffffffu, ar1, 1);
-        ar2 = __shfl_up_sync(0xffffffffu, ar2, 1);
-        g0 = __shfl_up_sync(0xffffffffu, g0, 1);
-        g1 = __shfl_up_sync(0xffffffffu, g1, 1);
-        g2 = __shfl_up_sync(0xffffffffu, g2, 1);
-        nc = __shfl_up_sync(0xffffffffu, nc, 1);
-        if (lane == 0) {
-            if (i < TILE_PIX) {
-                const int s = i & 31;
-                T = sp[0][s]; ar0 = sp[1][s]; ar1 = sp[2][s]; ar2 = sp[3][s];
-                g0 = sp[4][s]; g1 = sp[5][s]; g2 = sp[6][s]; nc = __float_as_int(sp[7][s]);
-            } else {
-                nc = 0;
-            }
+        if (valid_splat) {
+            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx);
+            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my);
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx);
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy);
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw);
+            atomicAdd(&dL_dopacity[gid], acc_o);
+            atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], acc_c0);
+            atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], acc_c1);
+            atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], acc_c2);
         }
-        const int p = i - lane;
-        if (valid_splat && p >= 0 && p < TILE_PIX && splat_in_tile < nc) {
-            const float pfx = (float)(pix_min_x + (p & (TILE - 1))), pfy = (float)(pix_min_y + (p >> 4));
-            const float dx = fsub(mx, pfx), dy = fsub(my, pfy);
-            const float power = splat_power(dx, dy, cx, cy, cz);
-            if (power > 0.0f) continue;
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, fmul(op, G));
-            if (alpha < (1.0f / 255.0f)) continue;
-            const float dchannel_dcolor = alpha * T;
-            const float alpha_inverse = 1.0f / (1.0f - alpha);
-            float dL_dalpha;
-            ar0 += T * alpha * c0; acc_c0 += dchannel_dcolor * g0; dL_dalpha = ((c0 * T) - alpha_inverse * (-ar0)) * g0;
-            ar1 += T * alpha * c1; acc_c1 += dchannel_dcolor * g1; dL_dalpha += ((c1 * T) - alpha_inverse * (-ar1)) * g1;
-            ar2 += T * alpha * c2; acc_c2 += dchannel_dcolor * g2; dL_dalpha += ((c2 * T) - alpha_inverse * (-ar2)) * g2;
-            T = fmul(T, fsub(1.0f, alpha));
-            const float dL_dG = op * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * cx - gdy * cy;
-            const float dG_ddely = -gdy * cz - gdx * cy;
-            acc_mx += dL_dG * dG_ddelx * ddelx_dx;
-            acc_my += dL_dG * dG_ddely * ddely_dy;
-            acc_cx += -0.5f * gdx * dx * dL_dG;
-            acc_cy += -0.5f * gdx * dy * dL_dG;
-            acc_cw += -0.5f * gdy * dy * dL_dG;
-            acc_o += G * dL_dalpha;
-        }
-    }
-    if (valid_splat) {
-        atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx);
-        atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my);
-        atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx);
-        atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy);
-        atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw);
-        atomicAdd(&dL_dopacity[gid], acc_o);
-        atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], acc_c0);
-        atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], acc_c1);
-        atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], acc_c2);
+        __syncwarp();
     }
 }
 
@@ -359,13 +412,23 @@ int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* p
 int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,
                            ImageState img, SampleState smp, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
                            float* dL_dopacity, float* dL_dcolors, cudaStream_t s) {
-    (void)P;
+    (void)P; (void)smp.bucket_to_tile;
     if (max_buckets <= 0) return GLIC_OK;
-    const unsigned blocks = (unsigned)((max_buckets + BWD_WARPS - 1) / BWD_WARPS);
-    render_backward_kernel<<<blocks, BWD_WARPS * 32, 0, s>>>(
-        vp, img.hdr, img.ranges, point_list, g.rec, img.bucket_offsets, smp.bucket_to_tile,
-        smp.ckpt, img.n_contrib, img.max_contrib, img.pixel_colors, dL_dpix,
-        dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
+    const int T = vp.grid_x * vp.grid_y;
+    live_scan_kernel<<<1, 1024, 0, s>>>(T, img.max_contrib, img.live_offsets, img.hdr);
+    GLIC_LAUNCH_CHECK();
+    static int blocks = 0;
+    if (blocks == 0) {
+        int dev = 0, sms = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_backward_kernel, BWD_WARPS * 32, 0);
+        blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int64_t need = (max_buckets + BWD_WARPS - 1) / BWD_WARPS;
+    render_backward_kernel<<<(unsigned)std::min<int64_t>(blocks, need), BWD_WARPS * 32, 0, s>>>(
+        vp, T, img.hdr, img.ranges, point_list, g.rec, img.bucket_offsets, img.live_offsets, smp.ckpt, img.n_contrib,
+        img.pixel_colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }
