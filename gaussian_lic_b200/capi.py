@@ -46,6 +46,9 @@ def _load():
         "glic_knn_temp_bytes": (sz, [i32]),
         "glic_forward_preprocess": (i32, [i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, C.POINTER(View), i32, vp, vp, sz,
                                           vp, sz, C.POINTER(i64), vp]),
+        "glic_binning_capacity": (i64, [sz, sz, i32, i32, i32]),
+        "glic_forward": (i32, [i32, i32, i32, vp, vp, f32, vp, vp, vp, vp, C.POINTER(View), i32, vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp,
+                               vp, vp]),
         "glic_forward_render": (i32, [i32, C.POINTER(View), i32, i64, vp, vp, vp, sz, vp, sz, vp, vp, C.POINTER(i64), vp]),
         "glic_backward": (i32, [i32, i32, i32, vp, vp, f32, vp, vp, vp, C.POINTER(View), vp, i64, vp, vp, vp, vp, vp, f32,
                                 vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -134,7 +134,7 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
         StageTimer _t(GLIC_STAGE_SORT, s);
         const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
         if (cur < 0) return cur;
-        if (int e = launch_depth_scan(P, g, g.order[cur], s)) return e;
+        if (int e = launch_depth_scan(P, g, g.order[cur], 0xFFFFFFFFll, s)) return e;
     }
     unsigned int total = 0;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&total, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -169,7 +169,7 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
 
     int cur = 0;
     if (R > 0) {
-        { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], s)) return e; }
+        { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], R, s)) return e; }
         const int bit = (int)higher_msb((uint32_t)T);                       // rasterizer_impl.cu:417
         // pairs arrive ordered by (depth, index): a stable sort on the tile bits alone finishes the job
         { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs32(R, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
@@ -177,7 +177,7 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
     }
     const unsigned int flag = (unsigned int)cur;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
-    { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, bin.keys[cur], T, img, !no_color, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, nullptr, nullptr, bin.keys[cur], T, img, !no_color, s)) return e; }
     { StageTimer _t(GLIC_STAGE_RENDER_FWD, s); if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
     if (num_buckets_host) {
         unsigned int nb = 0;
@@ -185,6 +185,73 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
         GLIC_CUDA_TRY(cudaStreamSynchronize(s));
         *num_buckets_host = nb;
     }
+    return GLIC_OK;
+}
+
+int64_t glic_binning_capacity(size_t binning_bytes, size_t sample_bytes, int width, int height, int no_color) {
+    // largest R whose workspaces fit: both size functions are monotone in R
+    int64_t lo = 0, hi = (int64_t)1 << 31;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        const bool fits = glic_binning_bytes(mid) <= binning_bytes && (no_color || glic_sample_bytes(mid, width, height) <= sample_bytes);
+        if (fits) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+int glic_forward(int P, int sh_degree, int M, const float* means3D, const float* scales, float scale_modifier,
+                 const float* rotations, const float* opacities, const float* dc, const float* sh, const glic_view* view,
+                 int no_color, int* radii, void* geom_ws, size_t geom_bytes, void* image_ws, size_t image_bytes, void* binning_ws,
+                 size_t binning_bytes, void* sample_ws, size_t sample_bytes, float* out_color, float* out_final_T,
+                 int64_t* counters_host, void* stream) {
+    if (int e = check_view(view)) return e;
+    if (P < 0 || sh_degree < 0 || sh_degree > 3 || M < 0) { set_error("forward: bad P / sh_degree / M"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (!no_color && (sh_degree + 1) * (sh_degree + 1) - 1 > M) { set_error("forward: sh has fewer coefficients than sh_degree needs"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (!image_ws || image_bytes < glic_image_bytes(view->width, view->height)) { set_error("forward: image workspace too small"); return GLIC_ERR_WORKSPACE; }
+    if (!out_final_T || (!no_color && !out_color)) { set_error("forward: null output"); return GLIC_ERR_INVALID_ARGUMENT; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const ViewParams vp = make_view_params(view);
+    const int T = vp.grid_x * vp.grid_y;
+    const size_t HW = (size_t)vp.W * vp.H;
+    ImageState img = ImageState::carve(image_ws, vp.W, vp.H);
+    if (P == 0) {
+        GLIC_CUDA_TRY(cudaMemsetAsync(out_final_T, 0, sizeof(float) * HW, s));
+        if (out_color) GLIC_CUDA_TRY(cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * HW, s));
+        GLIC_CUDA_TRY(cudaMemsetAsync(img.hdr, 0, sizeof(ImageHeader), s));
+        if (counters_host) GLIC_CUDA_TRY(cudaMemcpyAsync(counters_host, img.hdr->counters, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        return GLIC_OK;
+    }
+    if (!means3D || !scales || !rotations || !opacities || !radii || (!no_color && (!dc || (M > 0 && sh_degree > 0 && !sh)))) {
+        set_error("forward: null input pointer"); return GLIC_ERR_INVALID_ARGUMENT;
+    }
+    if (!aligned16(rotations)) { set_error("forward: rotations must be 16-byte aligned"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (!geom_ws || geom_bytes < glic_geom_bytes(P)) { set_error("forward: geometry workspace too small"); return GLIC_ERR_WORKSPACE; }
+    const int64_t cap = glic_binning_capacity(binning_bytes, sample_bytes, vp.W, vp.H, no_color);
+    if (!binning_ws || cap < 1 || (!no_color && !sample_ws)) { set_error("forward: binning / sample workspace missing or too small"); return GLIC_ERR_WORKSPACE; }
+    GeomState g = GeomState::carve(geom_ws, P);
+    BinningState bin = BinningState::carve(binning_ws, cap);
+    const int64_t max_buckets = no_color ? 0 : glic_max_buckets(cap, vp.W, vp.H);
+    SampleState smp = SampleState::carve(no_color ? nullptr : sample_ws, max_buckets);
+    { StageTimer _t(GLIC_STAGE_PREPROCESS, s);
+      if (int e = launch_preprocess_forward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, opacities, dc, sh, vp,
+                                            no_color != 0, radii, g, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_SORT, s);
+      const int cur0 = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
+      if (cur0 < 0) return cur0;
+      if (int e = launch_depth_scan(P, g, g.order[cur0], cap, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], cap, s)) return e; }
+    int cur;
+    { StageTimer _t(GLIC_STAGE_SORT, s);
+      const int bit = (int)higher_msb((uint32_t)T);
+      cur = launch_sort_pairs32(cap, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s, &g.hdr->r_eff);
+      if (cur < 0) return cur; }
+    const unsigned int flag = (unsigned int)cur;
+    GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+    { StageTimer _t(GLIC_STAGE_RANGES, s);
+      if (int e = launch_tile_ranges(cap, &g.hdr->r_eff, &g.hdr->overflow, bin.keys[cur], T, img, !no_color, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_RENDER_FWD, s);
+      if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
+    if (counters_host) GLIC_CUDA_TRY(cudaMemcpyAsync(counters_host, img.hdr->counters, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s));
     return GLIC_OK;
 }
 

@@ -78,7 +78,9 @@ struct GeomHeader {
     unsigned int total;         // R = sum of tiles_touched
     unsigned int visible;       // #Gaussians with radius > 0
     unsigned int order_cur;     // which ping-pong half holds the depth-sorted order
-    unsigned int pad[28];
+    unsigned int r_eff;         // min(R, capacity of the binning workspace): what the sort / ranges / render use
+    unsigned int overflow;      // 1 when R exceeded the capacity (frame invalid, caller re-runs with more room)
+    unsigned int pad[26];
 };
 
 size_t sort_temp_bytes(int64_t n);
@@ -119,7 +121,9 @@ struct ImageHeader {
     long long num_rendered;     // R
     unsigned int num_buckets;   // B
     unsigned int num_live_buckets;   // buckets some pixel reached (backward work list)
-    unsigned int pad[28];
+    unsigned int pad0;
+    long long counters[4];      // {R, B, overflow, 0}: copied to the host asynchronously by glic_forward
+    unsigned int pad[20];
 };
 
 struct ImageState {
@@ -225,14 +229,17 @@ inline ViewParams make_view_params(const glic_view* v) {
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
                               const float* rots, const float* opac, const float* dc, const float* sh,
                               const ViewParams& vp, bool no_color, int* radii, GeomState g, cudaStream_t s);
-int launch_depth_scan(int P, GeomState g, const uint32_t* order, cudaStream_t s);
-int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
+int launch_depth_scan(int P, GeomState g, const uint32_t* order, int64_t capacity, cudaStream_t s);
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, cudaStream_t s);
 // Sorts on bits [0,end_bit); returns 0/1 = index of the ping-pong buffer holding the result, <0 on error.
 int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
                       cudaStream_t s);
+// n_dev (optional): device-side true count <= n; kernels are launched for n (a capacity) and clip to *n_dev.
 int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                        cudaStream_t s);
-int launch_tile_ranges(int64_t R, const uint32_t* tile_keys_sorted, int T, ImageState img, bool buckets, cudaStream_t s);
+                        cudaStream_t s, const unsigned int* n_dev = nullptr);
+// R: host-side count or capacity; r_dev (optional): device-side true count
+int launch_tile_ranges(int64_t R, const unsigned int* r_dev, const unsigned int* overflow_dev, const uint32_t* tile_keys_sorted, int T,
+                       ImageState img, bool buckets, cudaStream_t s);
 int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* point_list, GeomState g, ImageState img,
                           SampleState smp, float* out_color, float* out_final_T, cudaStream_t s);
 int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,

@@ -17,6 +17,7 @@
 //   * every key-defining operation uses the fixed-order intrinsics of geom_math.cuh.
 #include "geom_math.cuh"
 #include "warp_rows.cuh"
+#include <algorithm>
 
 namespace glic {
 
@@ -343,7 +344,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
 // few loads, so no CTA ever delays its successors): Gaussian order[pos] owns slots [end - tiles, end) and
 // `end` is scattered to offsets[gaussian] so that the emit kernel can run in (well mixed) index order.
 __global__ void __launch_bounds__(PRE_THREADS)
-depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order) {
+depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsigned int capacity) {
     __shared__ unsigned s_block;
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
     __shared__ uint32_t s_block_excl;
@@ -373,7 +374,14 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order) {
         const uint32_t aggregate = __shfl_sync(0xffffffffu, wi, PRE_THREADS / 32 - 1);
         if (lane < PRE_THREADS / 32) s_warp_sum[lane] = wi - ws;      // exclusive per-warp base
         const uint32_t excl = lookback_exclusive(g.scan_status, block, aggregate, lane);
-        if (lane == 0) s_block_excl = excl;
+        if (lane == 0) {
+            s_block_excl = excl;
+            if (block == (int)gridDim.x - 1) {              // the last ticket sees the grand total
+                const unsigned int total = excl + aggregate;
+                g.hdr->r_eff = min(total, capacity);
+                g.hdr->overflow = total > capacity ? 1u : 0u;
+            }
+        }
     }
     __syncthreads();
     if (pos < P) g.offsets[gid] = s_block_excl + s_warp_sum[warp] + incl;
@@ -382,19 +390,22 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order) {
 // Key emission in index order: Gaussian idx re-walks its rect with the same exact test and writes
 // key = tile id, value = idx into its slot range [offsets[idx] - tiles, offsets[idx]).
 __global__ void __launch_bounds__(PRE_THREADS)
-emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned int capacity) {
     __shared__ WalkSmem walk;
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     int n = 0, x0 = 0, y0 = 0, rw = 1;
     float mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, thr = 0.f;
     uint32_t off = 0;
+    bool skip = false;
     if (idx < P) {
         const uint32_t tiles = g.tiles[idx];
         if (tiles != 0) {
             const float4 r0 = g.rec[3 * (size_t)idx + 0];
             const float4 r1 = g.rec[3 * (size_t)idx + 1];
             const float4 r2 = g.rec[3 * (size_t)idx + 2];
-            off = g.offsets[idx] - tiles;
+            const uint32_t end = g.offsets[idx];
+            off = end - tiles;
+            if (end > capacity) { skip = true; }           // would overrun the workspace: overflow is flagged by the scan
             mx = r0.x; my = r0.y; cox = r0.z; coy = r0.w; coz = r1.x;
             const TileRect rc = tile_rect(mx, my, __float_as_int(r2.z), vp.grid_x, vp.grid_y);
             thr = logf(__fdiv_rn(r1.y, 1.0f / 255.0f));
@@ -402,7 +413,7 @@ emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys,
             n = (rc.y1 - rc.y0) * rw;
         }
     }
-    block_tile_walk<true>(walk, n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals);
+    block_tile_walk<true>(walk, skip ? 0 : n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals);
 }
 
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
@@ -425,14 +436,16 @@ int launch_preprocess_forward(int P, int D, int M, const float* means, const flo
     return GLIC_OK;
 }
 
-int launch_depth_scan(int P, GeomState g, const uint32_t* order, cudaStream_t s) {
-    depth_scan_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, g, order);
+int launch_depth_scan(int P, GeomState g, const uint32_t* order, int64_t capacity, cudaStream_t s) {
+    const unsigned int cap = (unsigned int)std::min<int64_t>(capacity, 0xFFFFFFFFll);
+    depth_scan_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, g, order, cap);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }
 
-int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s) {
-    emit_keys_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, vp, g, tile_keys, vals);
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, cudaStream_t s) {
+    const unsigned int cap = (unsigned int)std::min<int64_t>(capacity, 0xFFFFFFFFll);
+    emit_keys_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, vp, g, tile_keys, vals, cap);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

@@ -61,7 +61,9 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 // ---- 1. all-pass histogram --------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-sort_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int passes, int end_bit, uint32_t* __restrict__ hist) {
+sort_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, const unsigned int* __restrict__ n_dev, int passes, int end_bit,
+                      uint32_t* __restrict__ hist) {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
     __shared__ uint32_t sh[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -116,8 +118,9 @@ struct __align__(16) PassSmem {
 template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
-                     const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, const unsigned int* __restrict__ n_dev,
+                     int shift, int bits, const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status,
+                     uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PassSmem<KeyT>& sm = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,8 +129,10 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
     if (tid == 0) sm.block_id = atomicAdd(ticket, 1u);
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.warp_cnt[0][0])[i] = 0;
     __syncthreads();
+    if (n_dev) n = min(n, (int64_t)*n_dev);   // capacity-sized launch: the true count lives on the device
     const int64_t block = sm.block_id;
     const int64_t tile_base = block * SORT_TILE;
+    if (tile_base >= n) return;                 // (CTA-uniform) nothing for this ticket
     const int count = (int)min((int64_t)SORT_TILE, n - tile_base);
 
     // -- load (warp-striped: lane l, item j <-> element warp*512 + j*32 + l; order-preserving)
@@ -257,7 +262,7 @@ size_t sort_temp_bytes(int64_t n) {
 
 template <typename KeyT>
 static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                               cudaStream_t s) {
+                               cudaStream_t s, const unsigned int* n_dev = nullptr) {
     if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
     if (n >= (int64_t)VALUE_MASK) { set_error("sort: n too large"); return GLIC_ERR_INVALID_ARGUMENT; }
     if (n <= 0) return 0;
@@ -276,7 +281,7 @@ static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* 
         attr_set = true;
     }
     int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
-    sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, passes, end_bit, t.hist);
+    sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, n_dev, passes, end_bit, t.hist);
     GLIC_LAUNCH_CHECK();
     sort_scan_hist_kernel<<<passes, RADIX, 0, s>>>(t.hist);
     GLIC_LAUNCH_CHECK();
@@ -285,7 +290,7 @@ static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* 
         const int shift = p * RADIX_BITS;
         const int bits = min(RADIX_BITS, end_bit - shift);
         onesweep_pass_kernel<KeyT><<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem<KeyT>), s>>>(
-            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, bits, t.hist + p * RADIX,
+            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev, shift, bits, t.hist + p * RADIX,
             t.status + (size_t)p * blocks * RADIX, t.tickets + p);
         GLIC_LAUNCH_CHECK();
         cur ^= 1;
@@ -299,8 +304,8 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
 }
 
 int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                        cudaStream_t s) {
-    return launch_sort_pairs_t<uint32_t>(n, end_bit, keys, vals, temp, temp_bytes, s);
+                        cudaStream_t s, const unsigned int* n_dev) {
+    return launch_sort_pairs_t<uint32_t>(n, end_bit, keys, vals, temp, temp_bytes, s, n_dev);
 }
 
 }  // namespace glic

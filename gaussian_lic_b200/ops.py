@@ -190,12 +190,15 @@ class CRasterizer:
         self.R = 0
         self.B = 0
         self.P = 0
+        self.cap = 0            # capacity (pairs) the binning / sample workspaces are carved with
+        self.cap_target = 0
+        self.counters = torch.zeros(3, dtype=torch.int64).pin_memory() if torch.cuda.is_available() else torch.zeros(3, dtype=torch.int64)
         self._view_keep = None
 
-    def _grow(self, name, nbytes):
+    def _grow(self, name, nbytes, slack=1.25):
         t = getattr(self, name)
         if t.numel() < nbytes:
-            setattr(self, name, torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.dev))
+            setattr(self, name, torch.empty(int(nbytes * slack) + 256, dtype=torch.uint8, device=self.dev))
         return getattr(self, name)
 
     def make_view(self, cam):
@@ -209,10 +212,11 @@ class CRasterizer:
         self._view_keep = (v, p, c)
         return view
 
-    def forward(self, g, view, no_color=False, scale_modifier=1.0, out_color=None, out_T=None, radii=None,
-                sync_buckets=True):
-        """g: dict of device tensors means[P,3] scales[P,3] rots[P,4] opacity[P] dc[P,3] sh[P,M,3] + degree."""
-        lib, st = self.lib, None
+    def forward(self, g, view, no_color=False, scale_modifier=1.0, out_color=None, out_T=None, radii=None, sync=True):
+        """One asynchronous glic_forward call.  g: dict of device tensors means[P,3] scales[P,3] rots[P,4] opacity[P]
+        dc[P,3] sh[P,M,3] + degree.  The binning / sample workspaces are sized by a capacity that grows on overflow;
+        with sync=False nothing blocks (call finish() before trusting R/B or after a scene change)."""
+        lib = self.lib
         P = int(g["means"].shape[0])
         M = int(g["sh"].shape[1]) if g["sh"].numel() else 0
         self.P, self.M, self.D = P, M, int(g["degree"])
@@ -221,24 +225,35 @@ class CRasterizer:
         out_T = torch.empty(self.H, self.W, **f32) if out_T is None else out_T
         radii = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev) if radii is None else radii
         self._grow("geom_ws", lib.glic_geom_bytes(P))
-        R = C.c_int64(0)
-        capi.check(lib.glic_forward_preprocess(
-            P, self.D, M, capi.ptr(g["means"]), capi.ptr(g["scales"]), scale_modifier, capi.ptr(g["rots"]),
-            capi.ptr(g["opacity"]), capi.ptr(g["dc"]), capi.ptr(g["sh"]) if M else None, C.byref(view), int(no_color),
-            capi.ptr(radii), capi.ptr(self.geom_ws), self.geom_ws.numel(), capi.ptr(self.image_ws),
-            self.image_ws.numel(), C.byref(R), st), "forward_preprocess")
-        self.R = int(R.value)
-        self._grow("binning_ws", lib.glic_binning_bytes(self.R))
-        if not no_color:
-            self._grow("sample_ws", lib.glic_sample_bytes(self.R, self.W, self.H))
-        B = C.c_int64(0)
-        capi.check(lib.glic_forward_render(
-            P, C.byref(view), int(no_color), self.R, capi.ptr(self.geom_ws), capi.ptr(self.image_ws),
-            capi.ptr(self.binning_ws), self.binning_ws.numel(), None if no_color else capi.ptr(self.sample_ws),
-            self.sample_ws.numel(), capi.ptr(out_color), capi.ptr(out_T), C.byref(B) if sync_buckets else None, st),
-            "forward_render")
-        self.B = int(B.value)
+        if self.cap_target == 0:
+            self.cap_target = max(8 * P, 1 << 16)
+        while True:
+            self._grow("binning_ws", lib.glic_binning_bytes(self.cap_target), slack=1.0)
+            if not no_color:
+                self._grow("sample_ws", lib.glic_sample_bytes(self.cap_target, self.W, self.H), slack=1.0)
+            self.cap = int(lib.glic_binning_capacity(self.binning_ws.numel(), self.sample_ws.numel(), self.W, self.H, int(no_color)))
+            capi.check(lib.glic_forward(
+                P, self.D, M, capi.ptr(g["means"]), capi.ptr(g["scales"]), scale_modifier, capi.ptr(g["rots"]),
+                capi.ptr(g["opacity"]), capi.ptr(g["dc"]), capi.ptr(g["sh"]) if M else None, C.byref(view), int(no_color),
+                capi.ptr(radii), capi.ptr(self.geom_ws), self.geom_ws.numel(), capi.ptr(self.image_ws),
+                self.image_ws.numel(), capi.ptr(self.binning_ws), self.binning_ws.numel(),
+                None if no_color else capi.ptr(self.sample_ws), self.sample_ws.numel(), capi.ptr(out_color), capi.ptr(out_T),
+                capi.ptr(self.counters), None), "forward")
+            if not sync:
+                break
+            if not self.finish():
+                break
         return out_color, out_T, radii[:P]
+
+    def finish(self):
+        """Synchronise, publish R / B, and grow the capacity if the last forward overflowed (returns True then)."""
+        torch.cuda.synchronize(self.dev)
+        R, B, ovf = (int(x) for x in self.counters.tolist())
+        self.R, self.B = R, B
+        if ovf:
+            self.cap_target = int(R * 1.25) + 4096
+            return True
+        return False
 
     def alloc_grads(self, P=None, M=None):
         P = self.P if P is None else P
@@ -254,7 +269,7 @@ class CRasterizer:
         grads = self.alloc_grads() if grads is None else grads
         capi.check(self.lib.glic_backward(
             self.P, self.D, self.M, capi.ptr(g["means"]), capi.ptr(g["scales"]), scale_modifier, capi.ptr(g["rots"]),
-            capi.ptr(g["dc"]), capi.ptr(g["sh"]) if self.M else None, C.byref(view), capi.ptr(radii), self.R,
+            capi.ptr(g["dc"]), capi.ptr(g["sh"]) if self.M else None, C.byref(view), capi.ptr(radii), self.cap,
             capi.ptr(self.geom_ws), capi.ptr(self.binning_ws), capi.ptr(self.image_ws), capi.ptr(self.sample_ws),
             capi.ptr(dL_dpix), lambda_erank, capi.ptr(grads["dL_dmeans2D"]), capi.ptr(grads["dL_dconic"]),
             capi.ptr(grads["dL_dopacity"]), capi.ptr(grads["dL_dcolors"]), capi.ptr(grads["dL_dmeans3D"]),
@@ -273,7 +288,7 @@ class CRasterizer:
 
     # ---- introspection for parity tests -------------------------------------------------------------------
     def debug_state(self):
-        lib, P, R, W, H = self.lib, self.P, self.R, self.W, self.H
+        lib, P, R, W, H = self.lib, self.P, self.cap, self.W, self.H
         T = ((W + 15) // 16) * ((H + 15) // 16)
         dev = self.dev
         d = dict(depth=torch.empty(P, device=dev), xy=torch.empty(P, 2, device=dev),
@@ -298,6 +313,7 @@ class CRasterizer:
                                         capi.ptr(d["max_contrib"]), cnt, None), "debug_image")
         torch.cuda.synchronize(dev)
         d["R"], d["B"] = int(cnt[0]), int(cnt[1])
+        d["point_list"], d["keys_sorted"] = d["point_list"][:d["R"]], d["keys_sorted"][:d["R"]]
         return d
 
 

@@ -106,6 +106,26 @@ GLIC_API int glic_forward_render(int P, const glic_view* view, int no_color, int
                         void* sample_ws, size_t sample_bytes, float* out_color, float* out_final_T,
                         int64_t* num_buckets_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Forward in ONE asynchronous call (no host synchronisation inside): the same stages as
+ * glic_forward_preprocess + glic_forward_render, but the binning / sample workspaces are sized by
+ * the CALLER'S CAPACITY instead of the exact num_rendered, which therefore never has to travel
+ * to the host mid-frame (the reference blocks twice per forward, rasterizer_impl.cu:398,442).
+ *   capacity = glic_binning_capacity(binning_bytes, sample_bytes, W, H, no_color) pairs.
+ *   counters_host[3] = {R, B, overflow} is written ASYNCHRONOUSLY (use pinned memory); it is valid
+ *   once `stream` has been synchronised.  overflow != 0 means R exceeded the capacity: the
+ *   images are invalid and the call must be repeated with workspaces for at least R pairs.
+ *   For glic_backward pass num_rendered = that same capacity (the value the workspaces were
+ *   carved with), not R.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int64_t glic_binning_capacity(size_t binning_bytes, size_t sample_bytes, int width, int height, int no_color);
+GLIC_API int glic_forward(int P, int sh_degree, int M, const float* means3D, const float* scales, float scale_modifier,
+                          const float* rotations, const float* opacities, const float* dc, const float* sh,
+                          const glic_view* view, int no_color, int* radii, void* geom_ws, size_t geom_bytes,
+                          void* image_ws, size_t image_bytes, void* binning_ws, size_t binning_bytes, void* sample_ws,
+                          size_t sample_bytes, float* out_color, float* out_final_T, int64_t* counters_host,
+                          void* stream);
+
 /* Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:476-580;
  * backward.cu:138-597) AND the ten torch::zeros of rasterize_points.cu:192-201: every output
  * element is written (exact zeros for culled Gaussians), nothing needs pre-zeroing.
