@@ -325,9 +325,10 @@ int glic_debug_geom(int P, const void* geom_ws, float* depth, float* xy, float* 
     return GLIC_OK;
 }
 
-int glic_debug_binning(int P, const void* geom_ws, int64_t R, const void* binning_ws, uint32_t* point_list, uint64_t* keys_sorted,
-                       void* stream) {
-    if (R <= 0) return GLIC_OK;
+int glic_debug_binning(int P, const void* geom_ws, int64_t R, int64_t count, const void* binning_ws, uint32_t* point_list,
+                       uint64_t* keys_sorted, void* stream) {
+    if (R <= 0 || count <= 0) return GLIC_OK;
+    if (count > R) { set_error("debug_binning: count exceeds the carve size"); return GLIC_ERR_INVALID_ARGUMENT; }
     if (!binning_ws || !geom_ws) { set_error("debug_binning: null workspace"); return GLIC_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     BinningState bin = BinningState::carve(const_cast<void*>(binning_ws), R);
@@ -336,9 +337,9 @@ int glic_debug_binning(int P, const void* geom_ws, int64_t R, const void* binnin
     GLIC_CUDA_TRY(cudaMemcpyAsync(&cur, &bin.hdr->sorted_in_b, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     GLIC_CUDA_TRY(cudaStreamSynchronize(s));
     cur &= 1u;
-    if (point_list) GLIC_CUDA_TRY(cudaMemcpyAsync(point_list, bin.vals[cur], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    if (point_list) GLIC_CUDA_TRY(cudaMemcpyAsync(point_list, bin.vals[cur], sizeof(uint32_t) * (size_t)count, cudaMemcpyDeviceToDevice, s));
     if (keys_sorted) {   // the 64-bit (tile|depth) key of the reference, rebuilt from the tile key and the record's depth
-        debug_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((long long)R, g, bin.keys[cur], bin.vals[cur], keys_sorted);
+        debug_keys_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>((long long)count, g, bin.keys[cur], bin.vals[cur], keys_sorted);
         GLIC_LAUNCH_CHECK();
     }
     return GLIC_OK;

@@ -288,7 +288,7 @@ class CRasterizer:
 
     # ---- introspection for parity tests -------------------------------------------------------------------
     def debug_state(self):
-        lib, P, R, W, H = self.lib, self.P, self.cap, self.W, self.H
+        lib, P, R, W, H = self.lib, self.P, self.R, self.W, self.H
         T = ((W + 15) // 16) * ((H + 15) // 16)
         dev = self.dev
         d = dict(depth=torch.empty(P, device=dev), xy=torch.empty(P, 2, device=dev),
@@ -305,7 +305,7 @@ class CRasterizer:
         capi.check(lib.glic_debug_geom(P, capi.ptr(self.geom_ws), capi.ptr(d["depth"]), capi.ptr(d["xy"]),
                                        capi.ptr(d["conic_opacity"]), capi.ptr(d["rgb"]), capi.ptr(d["tiles_touched"]),
                                        capi.ptr(d["offsets"]), capi.ptr(d["clamped"]), None), "debug_geom")
-        capi.check(lib.glic_debug_binning(P, capi.ptr(self.geom_ws), R, capi.ptr(self.binning_ws), capi.ptr(d["point_list"]),
+        capi.check(lib.glic_debug_binning(P, capi.ptr(self.geom_ws), self.cap, R, capi.ptr(self.binning_ws), capi.ptr(d["point_list"]),
                                           capi.ptr(d["keys_sorted"]), None), "debug_binning")
         cnt = (C.c_int64 * 2)()
         capi.check(lib.glic_debug_image(W, H, capi.ptr(self.image_ws), capi.ptr(d["ranges"]),
@@ -313,7 +313,6 @@ class CRasterizer:
                                         capi.ptr(d["max_contrib"]), cnt, None), "debug_image")
         torch.cuda.synchronize(dev)
         d["R"], d["B"] = int(cnt[0]), int(cnt[1])
-        d["point_list"], d["keys_sorted"] = d["point_list"][:d["R"]], d["keys_sorted"][:d["R"]]
         return d
 
 

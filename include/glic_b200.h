@@ -198,7 +198,9 @@ GLIC_API int glic_knn_mean_dist2(int P, const float* points, float* mean_dists, 
  * ------------------------------------------------------------------------------------- */
 GLIC_API int glic_debug_geom(int P, const void* geom_ws, float* depth, float* xy, float* conic_opacity, float* rgb,
                     uint32_t* tiles_touched, uint32_t* offsets, uint8_t* clamped, void* stream);
-GLIC_API int glic_debug_binning(int P, const void* geom_ws, int64_t num_rendered, const void* binning_ws,
+/* num_rendered = the value the binning workspace was carved with (exact R, or the capacity after glic_forward);
+ * count = how many sorted entries to copy out (the true R). */
+GLIC_API int glic_debug_binning(int P, const void* geom_ws, int64_t num_rendered, int64_t count, const void* binning_ws,
                                 uint32_t* point_list, uint64_t* keys_sorted, void* stream);
 GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint32_t* ranges, uint32_t* bucket_offsets,
                      uint32_t* n_contrib, uint32_t* max_contrib, int64_t* counters2_host /* {R,B}, HOST pointer */, void* stream);
