@@ -177,7 +177,7 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
     }
     const unsigned int flag = (unsigned int)cur;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
-    { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, nullptr, nullptr, bin.keys[cur], T, img, !no_color, s)) return e; }
+    { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, nullptr, bin.keys[cur], T, img, !no_color, s)) return e; }
     { StageTimer _t(GLIC_STAGE_RENDER_FWD, s); if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
     if (num_buckets_host) {
         unsigned int nb = 0;
@@ -248,7 +248,7 @@ int glic_forward(int P, int sh_degree, int M, const float* means3D, const float*
     const unsigned int flag = (unsigned int)cur;
     GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
     { StageTimer _t(GLIC_STAGE_RANGES, s);
-      if (int e = launch_tile_ranges(cap, &g.hdr->r_eff, &g.hdr->overflow, bin.keys[cur], T, img, !no_color, s)) return e; }
+      if (int e = launch_tile_ranges(cap, g.hdr, bin.keys[cur], T, img, !no_color, s)) return e; }
     { StageTimer _t(GLIC_STAGE_RENDER_FWD, s);
       if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
     if (counters_host) GLIC_CUDA_TRY(cudaMemcpyAsync(counters_host, img.hdr->counters, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s));

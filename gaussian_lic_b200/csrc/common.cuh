@@ -78,7 +78,7 @@ struct GeomHeader {
     unsigned int total;         // R = sum of tiles_touched
     unsigned int visible;       // #Gaussians with radius > 0
     unsigned int order_cur;     // which ping-pong half holds the depth-sorted order
-    unsigned int r_eff;         // min(R, capacity of the binning workspace): what the sort / ranges / render use
+    unsigned int r_eff;         // R when it fits the binning workspace, else 0: what the sort / ranges / render use
     unsigned int overflow;      // 1 when R exceeded the capacity (frame invalid, caller re-runs with more room)
     unsigned int pad[26];
 };
@@ -238,8 +238,8 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
 int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
                         cudaStream_t s, const unsigned int* n_dev = nullptr);
 // R: host-side count or capacity; r_dev (optional): device-side true count
-int launch_tile_ranges(int64_t R, const unsigned int* r_dev, const unsigned int* overflow_dev, const uint32_t* tile_keys_sorted, int T,
-                       ImageState img, bool buckets, cudaStream_t s);
+int launch_tile_ranges(int64_t R, const GeomHeader* ghdr, const uint32_t* tile_keys_sorted, int T, ImageState img, bool buckets,
+                       cudaStream_t s);
 int launch_render_forward(const ViewParams& vp, bool no_color, const uint32_t* point_list, GeomState g, ImageState img,
                           SampleState smp, float* out_color, float* out_final_T, cudaStream_t s);
 int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, const uint32_t* point_list, GeomState g,

@@ -378,7 +378,8 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsign
             s_block_excl = excl;
             if (block == (int)gridDim.x - 1) {              // the last ticket sees the grand total
                 const unsigned int total = excl + aggregate;
-                g.hdr->r_eff = min(total, capacity);
+                // on overflow nothing downstream may touch the (partly unwritten) pair list: render an empty frame
+                g.hdr->r_eff = total > capacity ? 0u : total;
                 g.hdr->overflow = total > capacity ? 1u : 0u;
             }
         }

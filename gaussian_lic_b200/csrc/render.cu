@@ -49,7 +49,7 @@ tile_ranges_kernel(int64_t R, const unsigned int* __restrict__ r_dev, const uint
 // bucket_offsets = inclusive scan of ceil(n_t / 32); single CTA (T is a few thousand).
 __global__ void __launch_bounds__(1024)
 bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ bucket_offsets, ImageHeader* hdr,
-                   long long R, const unsigned int* __restrict__ r_dev, const unsigned int* __restrict__ overflow_dev, int buckets) {
+                   long long R, const GeomHeader* __restrict__ ghdr, int buckets) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,9 +84,10 @@ bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict
         __syncthreads();
     }
     if (tid == 0) {
-        if (r_dev) R = *r_dev;
+        long long true_R = R, ovf = 0;
+        if (ghdr) { R = ghdr->r_eff; true_R = ghdr->total; ovf = ghdr->overflow; }
         hdr->num_buckets = carry; hdr->num_rendered = R;
-        hdr->counters[0] = R; hdr->counters[1] = carry; hdr->counters[2] = overflow_dev ? (long long)*overflow_dev : 0; hdr->counters[3] = 0;
+        hdr->counters[0] = true_R; hdr->counters[1] = carry; hdr->counters[2] = ovf; hdr->counters[3] = 0;
     }
 }
 
@@ -393,14 +394,15 @@ render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr
 }
 
 // ---- launchers ------------------------------------------------------------------------------
-int launch_tile_ranges(int64_t R, const unsigned int* r_dev, const unsigned int* overflow_dev, const uint32_t* keys_sorted, int T,
-                       ImageState img, bool buckets, cudaStream_t s) {
+int launch_tile_ranges(int64_t R, const GeomHeader* ghdr, const uint32_t* keys_sorted, int T, ImageState img, bool buckets,
+                       cudaStream_t s) {
+    const unsigned int* r_dev = ghdr ? &ghdr->r_eff : nullptr;
     GLIC_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)T, s));
     if (R > 0) {
         tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, r_dev, keys_sorted, (uint32_t)T, img.ranges);
         GLIC_LAUNCH_CHECK();
     }
-    bucket_scan_kernel<<<1, 1024, 0, s>>>(T, img.ranges, img.bucket_offsets, img.hdr, (long long)R, r_dev, overflow_dev, buckets ? 1 : 0);
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(T, img.ranges, img.bucket_offsets, img.hdr, (long long)R, ghdr, buckets ? 1 : 0);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

@@ -144,3 +144,22 @@ def test_torch_shim_autograd_matches_capi(oracle32):
     o = g["opacity"].reshape(-1, 1)
     grad_close(op_logit.grad.cpu().numpy(), b["dL_dopacity"] * o * (1 - o), "d opacity-logit (shim)")
     oracle32.free(f)
+
+
+def test_capacity_overflow_recovers(oracle32):
+    """glic_forward sizes the pair list by a caller capacity; an undersized one must be flagged (empty frame, no
+    out-of-bounds access) and a retry with the reported R must reproduce the exact result."""
+    from gaussian_lic_b200 import ops
+    g, cam = small_scene(6000, 320, 208, 13, 3)
+    r = ops.CRasterizer(cam["W"], cam["H"])
+    gd = ops.scene_to_device(g)
+    view = r.make_view(cam)
+    r.cap_target = 1500                                   # far below R
+    color, T, radii = r.forward(gd, view, sync=False)
+    assert r.finish() is True and r.R > 1500              # overflow reported together with the true R
+    assert float(color.abs().max()) == 0.0 and float((T - 1.0).abs().max()) == 0.0   # empty frame, nothing read
+    color, T, radii = r.forward(gd, view)                 # sync=True retries until it fits
+    f = oracle32.forward(g, cam)
+    assert (r.R, r.B) == (f["R"], f["B"]) and r.cap >= r.R
+    image_close(color.cpu().numpy(), f["color"], "color after capacity growth")
+    oracle32.free(f)
