@@ -72,7 +72,7 @@ struct Carver {
 
 // Splat record, 48 bytes: three float4 per Gaussian (AoS so one gather = 1.5 sectors).
 //   r0 = (x, y, conic.x, conic.y)   r1 = (conic.z, opacity, red, green)
-//   r2 = (blue, depth, radius as int bits, tiles_touched as uint bits)
+//   r2 = (blue, depth, radius as int bits, hy = conservative vertical half-extent of the alpha >= 1/255 ellipse)
 struct GeomHeader {
     unsigned int ticket;        // dynamic CTA id of the emit kernel's fused scan
     unsigned int total;         // R = sum of tiles_touched

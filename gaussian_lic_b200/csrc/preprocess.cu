@@ -17,6 +17,7 @@
 //   * every key-defining operation uses the fixed-order intrinsics of geom_math.cuh.
 #include "geom_math.cuh"
 #include "warp_rows.cuh"
+#include "async_copy.cuh"
 #include <algorithm>
 
 namespace glic {
@@ -202,18 +203,36 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
     __syncthreads();
     const int block = (int)blockIdx.x;
     const int idx = block * PRE_THREADS + tid;
-    // coalesced 128-bit fetch of this warp's 32 SH rows; it lands while the geometry and the tile walk run
+    // The CTA's 256 SH rows are ONE contiguous run of HBM (up to 46 080 B): a single TMA bulk copy brings it into
+    // shared memory while the geometry and the tile walk run; threads wait on the mbarrier only when they need colour.
     const int K = 3 * M;
+    __shared__ __align__(8) uint64_t s_bar;
+    bool sh_tma = false, sh_staged = false;
     if (!no_color && D > 0 && K <= SH_ROW_MAX) {
-        const int wfirst = block * PRE_THREADS + warp * 32;
-        const int wcnt = min(32, P - wfirst);
-        if (wcnt > 0) warp_load_rows(sh, (size_t)wfirst, wcnt, K, s_sh[warp], lane);
+        const int bfirst = block * PRE_THREADS;
+        const int bcnt = min(PRE_THREADS, P - bfirst);
+        const size_t bytes = (size_t)bcnt * K * sizeof(float);
+        const float* src = sh + (size_t)bfirst * K;
+        sh_staged = bcnt > 0;
+        sh_tma = sh_staged && (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);   // CTA-uniform
+        if (sh_tma) {
+            if (tid == 0) {
+                mbar_init(&s_bar, 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&s_bar, (uint32_t)bytes);
+                bulk_copy_g2s(&s_sh[0][0], src, (uint32_t)bytes, &s_bar);
+            }
+        } else if (sh_staged) {                   // ragged tail / unaligned tensor: coalesced 128-bit loads per warp
+            const int wfirst = bfirst + warp * 32;
+            const int wcnt = min(32, P - wfirst);
+            if (wcnt > 0) warp_load_rows(sh, (size_t)wfirst, wcnt, K, s_sh[warp], lane);
+        }
     }
 
     uint32_t tiles = 0;
     int radius = 0;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    float blue = 0.f, depth = 0.f;
+    float blue = 0.f, depth = 0.f, hy = 0.f;
     unsigned clampbits = 0;
     // ---- phase 1: geometry of my Gaussian (fixed-order arithmetic) ----------------------------------
     float px = 0.f, py = 0.f, pz = 0.f, mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, o = 0.f, thr = 0.f, tz = 0.f;
@@ -253,6 +272,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
     // ---- phase 2: exact tile counting, balanced across the CTA --------------------------------------------
     const uint32_t cnt = block_tile_walk<false>(walk, n, mx, my, cox, coy, coz, thr, rx0, ry0, rw, vp.grid_x, 0u, 0u, nullptr, nullptr);
     // ---- phase 3: colour of the survivors -----------------------------------------------------------------
+    if (sh_tma) mbar_wait(&s_bar, 0);      // (the walk's __syncthreads order thread 0's barrier init before every wait)
     if (cnt > 0) {
         {
             {
@@ -269,7 +289,8 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) res[ch] = kSH_C0 * dc[3 * idx + ch];
                     if (D > 0) {
-                        const float* s = (K <= SH_ROW_MAX) ? (s_sh[warp] + lane * K) : (sh + (size_t)idx * K);
+                        const float* s = sh_tma ? (&s_sh[0][0] + (size_t)tid * K)
+                                                : (sh_staged ? (s_sh[warp] + lane * K) : (sh + (size_t)idx * K));
                         const float x = dx, y = dy, z = dz;
                         float b[15];
                         b[0] = -kSH_C1 * y; b[1] = kSH_C1 * z; b[2] = -kSH_C1 * x;
@@ -309,6 +330,14 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
                 }
                 r0 = make_float4(mx, my, cox, coy);
                 r1 = make_float4(coz, o, red, green);
+                // conservative vertical half-extent of {alpha >= 1/255} (dy^2 <= 2*thr*cox/det(conic)); falls back to the
+                // looser 3.33-sigma bound from the radius when det cancels badly.  Used by the render kernel's row cull.
+                {
+                    const float thr2 = __logf(255.0f * o) + 1e-3f;
+                    const float prod = cox * coz, dcon = prod - coy * coy;
+                    hy = 1.11f * (float)irad + 1.0f;
+                    if (dcon > 1e-3f * prod) hy = fminf(hy, sqrtf(2.0f * thr2 * cox / dcon) * 1.001f + 0.01f);
+                }
             }
         }
     }
@@ -329,7 +358,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         radii[idx] = radius;
         g.rec[3 * idx + 0] = r0;
         g.rec[3 * idx + 1] = r1;
-        g.rec[3 * idx + 2] = make_float4(blue, depth, __int_as_float(radius), __uint_as_float(tiles));
+        g.rec[3 * idx + 2] = make_float4(blue, depth, __int_as_float(radius), hy);
         g.clamped[idx] = (uint8_t)clampbits;
         g.tiles[idx] = tiles;
         g.depth_keys[0][idx] = tiles ? __float_as_uint(depth) : 0xFFFFFFFFu;   // culled Gaussians sort to the end

@@ -22,6 +22,7 @@
 // fixed-order intrinsics of geom_math.cuh, so colours/transmittance agree bit-for-bit with the
 // reference build on the same sorted list.
 #include "geom_math.cuh"
+#include "async_copy.cuh"
 #include <algorithm>
 
 namespace glic {
@@ -92,7 +93,10 @@ bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict
 }
 
 // ---- forward blend -------------------------------------------------------------------------
-struct __align__(8) StagedTail { float blue; uint32_t rowmask; };
+// Splat batches are staged by the TMA engine: every thread issues one 48-byte cp.async.bulk (its splat's
+// record, gathered by sorted index) into a double-buffered shared-memory tile buffer; an mbarrier per
+// buffer counts the bytes.  Batch i+1 is in flight while batch i is blended, no register staging.
+struct __align__(16) SplatRec { float4 a, b, c; };     // (x, y, conic.x, conic.y) (conic.z, opacity, r, g) (b, depth, radius, hy)
 
 __global__ void __launch_bounds__(TILE_PIX)
 render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ranges,
@@ -100,9 +104,8 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
                       const uint32_t* __restrict__ bucket_offsets, uint32_t* __restrict__ bucket_to_tile,
                       float4* __restrict__ ckpt, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
                       float* __restrict__ pixel_colors, float* __restrict__ out_color, float* __restrict__ out_T) {
-    __shared__ float4 s_a[TILE_PIX];        // x, y, conic.x, conic.y
-    __shared__ float4 s_b[TILE_PIX];        // conic.z, opacity, red, green
-    __shared__ StagedTail s_c[TILE_PIX];    // blue, row-pair mask
+    __shared__ SplatRec s_rec[2][TILE_PIX];
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_red[TILE_PIX / 32];
 
     const int tid = threadIdx.y * TILE + threadIdx.x;
@@ -117,47 +120,41 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
     const int n_splats = (int)(range.y - range.x);
     const int rounds = (n_splats + TILE_PIX - 1) / TILE_PIX;
 
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     uint32_t bbm = 0;
     if (!no_color) {
         bbm = tile == 0 ? 0u : bucket_offsets[tile - 1];
         const int nb = (n_splats + BUCKET - 1) / BUCKET;
         for (int b = tid; b < nb; b += TILE_PIX) bucket_to_tile[bbm + b] = tile;
     }
-    // rows of this warp (two tile rows) for the conservative row-pair cull
-    const uint32_t warp_bit = 1u << warp;
-    const float tile_y0 = (float)pix_min_y;
+    __syncthreads();
+    // issue the gather of batch `r` into buffer r & 1 (one 48-byte bulk copy per thread)
+    auto prefetch = [&](int r) {
+        const int cnt = min(TILE_PIX, n_splats - r * TILE_PIX);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[r & 1], (uint32_t)(cnt * sizeof(SplatRec)));
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + r * TILE_PIX + tid];
+            bulk_copy_g2s(&s_rec[r & 1][tid], rec + 3 * (size_t)id, (uint32_t)sizeof(SplatRec), &s_bar[r & 1]);
+        }
+    };
+    if (rounds > 0) prefetch(0);
+
+    // this warp covers tile rows 2w, 2w+1: splats whose alpha >= 1/255 ellipse cannot reach them are skipped
+    // warp-uniformly (conservative half-extent `hy` precomputed per splat => bit-identical results)
+    const float row_mid = (float)(pix_min_y + 2 * warp) + 0.5f;
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last_contributor = 0;
+    int waited = 0;                         // batches whose barrier this thread has consumed
 
     for (int i = 0; i < rounds; ++i) {
+        // everyone is past batch i-1 (its buffer may be refilled) -- and we may stop if all pixels are done
         if (__syncthreads_count(done) == TILE_PIX) break;
-        const int progress = i * TILE_PIX + tid;
-        if (progress < n_splats) {
-            const uint32_t id = point_list[range.x + progress];
-            const float4 r0 = rec[3 * (size_t)id + 0];
-            const float4 r1 = rec[3 * (size_t)id + 1];
-            const float4 r2 = rec[3 * (size_t)id + 2];
-            // conservative vertical half-extent of {alpha >= 1/255}: dy^2 <= 2*thr*cx/det(conic);
-            // falls back to the (looser) 3.33-sigma bound from the radius when det cancels badly.
-            const float thr = __logf(255.0f * r1.y) + 1e-3f;
-            const float prod = r0.z * r1.x;
-            const float det = prod - r0.w * r0.w;
-            float hy = 1.11f * (float)__float_as_int(r2.z) + 1.0f;
-            if (det > 1e-3f * prod) hy = fminf(hy, sqrtf(2.0f * thr * r0.z / det) * 1.001f + 0.01f);
-            uint32_t mask = 0;
-#pragma unroll
-            for (int w = 0; w < TILE_PIX / 32; ++w) {
-                const float row_lo = tile_y0 + (float)(2 * w), row_hi = row_lo + 1.0f;
-                if (!(row_lo > r0.y + hy || row_hi < r0.y - hy)) mask |= 1u << w;
-            }
-            s_a[tid] = r0;
-            s_b[tid] = r1;
-            StagedTail tl; tl.blue = r2.x; tl.rowmask = mask;
-            s_c[tid] = tl;
-        }
-        __syncthreads();
+        if (i + 1 < rounds) prefetch(i + 1);
+        mbar_wait(&s_bar[i & 1], (uint32_t)((i >> 1) & 1));
+        waited = i + 1;
+        const SplatRec* batch = s_rec[i & 1];
         const int nb = min(TILE_PIX, n_splats - i * TILE_PIX);
         if (!done) {
             for (int j = 0; j < nb; ++j) {
@@ -165,10 +162,10 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
                     ckpt[(size_t)bbm * TILE_PIX + tid] = make_float4(T, C0, C1, C2);
                     ++bbm;
                 }
-                const StagedTail tl = s_c[j];
-                if (!(tl.rowmask & warp_bit)) continue;               // warp-uniform skip
-                const float4 a = s_a[j];
-                const float4 b = s_b[j];
+                const float4 c = batch[j].c;
+                const float4 a = batch[j].a;
+                if (fabsf(row_mid - a.y) > c.w + 0.5f) continue;      // warp-uniform row-pair cull
+                const float4 b = batch[j].b;
                 const float dx = fsub(a.x, pfx), dy = fsub(a.y, pfy);
                 const float power = splat_power(dx, dy, a.z, a.w, b.x);
                 if (power > 0.0f) continue;
@@ -179,12 +176,17 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
                 if (!no_color) {
                     C0 = ffma(T, fmul(alpha, b.z), C0);
                     C1 = ffma(T, fmul(alpha, b.w), C1);
-                    C2 = ffma(T, fmul(alpha, tl.blue), C2);
+                    C2 = ffma(T, fmul(alpha, c.x), C2);
                 }
                 T = test_T;
                 last_contributor = (uint32_t)(i * TILE_PIX + j + 1);
             }
         }
+    }
+    // never leave the CTA with a bulk copy still in flight towards its shared memory
+    {
+        const int issued = min(rounds, waited + 1);
+        if (issued > waited) mbar_wait(&s_bar[waited & 1], (uint32_t)((waited >> 1) & 1));
     }
 
     if (inside) {
