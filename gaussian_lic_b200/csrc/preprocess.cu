@@ -78,23 +78,71 @@ GLIC_DI uint32_t lookback_exclusive(unsigned long long* status, int block, uint3
 
 // ---- load-balanced walk over the candidate tiles of a CTA's 256 Gaussians -------------------------------
 // Rect sizes span 1 .. 8160 tiles (median 4, 99th percentile ~900 at cfg2) and the big rects carry most of
-// the pairs.  Small rects (<= WALK_SMALL tiles) are walked by their own lane.  Big rects are compacted into a
-// shared-memory table and cut into 32-tile chunks that the CTA's 8 warps consume round-robin: one chunk = 32
-// consecutive tiles of ONE Gaussian (its parameters are warp-uniform), accepted tiles are counted / placed
-// with one shared-memory atomic per chunk.  EMIT writes key = tile id, value = Gaussian index into the
-// Gaussian's slot range; the order inside a slot range is arbitrary for big rects -- the tile ids of one
-// Gaussian are distinct, so the sorted list does not depend on it.
+// the pairs.  Small rects (<= WALK_SMALL tiles) are walked tile by tile by their own lane.  Big rects are
+// compacted into a shared-memory table and processed ROW by ROW, 32 rows per warp step: the accepted tiles
+// of one rect row form an interval (the tile test is the distance of a translating convex box to a convex
+// ellipse, quasi-convex along the row), so a lane predicts the interval analytically from the conic and
+// only runs the exact test at its two ends (~4 tests per row instead of one per tile).  The interval ends
+// are always decided by the exact fixed-order test, so the accept set is the reference's bit for bit.
+// EMIT writes key = tile id, value = Gaussian index into the Gaussian's slot range; the order inside a slot
+// range is arbitrary for big rects -- the tile ids of one Gaussian are distinct, so the sorted list does
+// not depend on it.
 constexpr int WALK_SMALL = 32;
 
 struct WalkSmem {
-    uint32_t chunk_prefix[PRE_THREADS + 1];   // exclusive prefix of chunk counts over the compacted big list
+    uint32_t row_prefix[PRE_THREADS + 1];     // exclusive prefix of row counts over the compacted big list
     uint32_t cursor[PRE_THREADS];             // accepted tiles so far, per big slot
     float mx[PRE_THREADS], my[PRE_THREADS], cox[PRE_THREADS], coy[PRE_THREADS], coz[PRE_THREADS], thr[PRE_THREADS];
     int x0[PRE_THREADS], y0[PRE_THREADS], rw[PRE_THREADS], n[PRE_THREADS];
     uint32_t off[PRE_THREADS], idx[PRE_THREADS];
     uint32_t warp_big[PRE_THREADS / 32];
-    uint32_t n_big, n_chunks;
+    uint32_t n_big, n_rows;
 };
+
+// Accepted tile interval [xa, xb] (inclusive; xa > xb = empty) of rect row `ty`, columns [x0, x1).
+GLIC_DI void row_span(float cox, float coy, float coz, float mx, float my, float thr, int ty, int x0, int x1, int& xa, int& xb) {
+    auto accept = [&](int x) { return tile_max_power(cox, coy, coz, mx, my, x, ty) <= thr; };
+    const float d0 = (float)(ty * TILE) - my, d1 = d0 + (float)(TILE - 1);      // dy range of the row's pixel centres
+    const float det = cox * coz - coy * coy;
+    const float t2 = 2.0f * thr;
+    int pa = x0, pb = x1 - 1;
+    bool predicted = false;
+    if (det > 0.0f && cox > 0.0f && coz > 0.0f && t2 >= 0.0f) {
+        // the slab misses the ellipse {power <= thr} by a clear margin: no tile of this row can pass the exact test
+        const float e0 = fminf(fmaxf(0.0f, d0), d1);
+        if (det * e0 * e0 > t2 * cox * 1.002f + 1e-6f) { xa = 1; xb = 0; return; }
+        // x-projection [xl, xr] of ellipse /\ slab (extreme points of the ellipse clamped into the slab)
+        const float hx = sqrtf(t2 * coz / det);
+        const float dyR = -coy * hx / coz;
+        float e = fminf(fmaxf(dyR, d0), d1);
+        const float xr = mx + (-coy * e + sqrtf(fmaxf(t2 * cox - det * e * e, 0.0f))) / cox;
+        e = fminf(fmaxf(-dyR, d0), d1);
+        const float xl = mx + (-coy * e - sqrtf(fmaxf(t2 * cox - det * e * e, 0.0f))) / cox;
+        if (xl == xl && xr == xr && fabsf(xl) < 1e7f && fabsf(xr) < 1e7f) {
+            pa = max(x0, min(x1 - 1, (int)ceilf((xl - (float)(TILE - 1)) * (1.0f / TILE))));
+            pb = max(x0, min(x1 - 1, (int)floorf(xr * (1.0f / TILE))));
+            predicted = pa <= pb;
+        }
+    }
+    int seed = -1;
+    if (predicted) { const int mid = (pa + pb) >> 1; if (accept(mid)) seed = mid; }
+    if (seed < 0) {                                   // rare: borderline / degenerate rows -> exact scan of the row
+        int l = x0;
+        while (l < x1 && !accept(l)) ++l;
+        if (l == x1) { xa = 1; xb = 0; return; }
+        int r = l;
+        while (r + 1 < x1 && accept(r + 1)) ++r;
+        xa = l; xb = r;
+        return;
+    }
+    int l = min(pa, seed);
+    if (accept(l)) { while (l > x0 && accept(l - 1)) --l; }
+    else { do { ++l; } while (l < seed && !accept(l)); }
+    int r = max(pb, seed);
+    if (accept(r)) { while (r + 1 < x1 && accept(r + 1)) ++r; }
+    else { do { --r; } while (r > seed && !accept(r)); }
+    xa = l; xb = r;
+}
 
 // Returns the number of accepted tiles of THIS thread's Gaussian.  Must be called by all PRE_THREADS threads.
 template <bool EMIT>
@@ -123,7 +171,7 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
         w.off[slot] = off; w.idx[slot] = idx;
         w.cursor[slot] = 0;
     }
-    // -- small rects: own lane, row-major
+    // -- small rects: own lane, row-major, every tile tested
     uint32_t count = 0;
     if (n > 0 && !big) {
         int tx = x0, ty = y0;
@@ -138,46 +186,68 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
     }
     __syncthreads();
     if (total_big == 0) return count;
-    // -- exclusive prefix of chunk counts over the compacted list (one warp; <= 256 entries)
+    // -- exclusive prefix of row counts over the compacted list (one warp; <= 256 entries)
     if (warp == 0) {
         uint32_t run = 0;
         for (uint32_t b0 = 0; b0 < total_big; b0 += 32) {
             const uint32_t s = b0 + lane;
-            const uint32_t c = s < total_big ? (uint32_t)((w.n[s] + 31) >> 5) : 0u;
+            const uint32_t c = s < total_big ? (uint32_t)(w.n[s] / w.rw[s]) : 0u;      // rect height
             uint32_t incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (s < total_big) w.chunk_prefix[s] = run + incl - c;
+            if (s < total_big) w.row_prefix[s] = run + incl - c;
             run += __shfl_sync(FULL, incl, 31);
         }
-        if (lane == 0) { w.chunk_prefix[total_big] = run; w.n_chunks = run; w.n_big = total_big; }
+        if (lane == 0) { w.row_prefix[total_big] = run; w.n_rows = run; w.n_big = total_big; }
     }
     __syncthreads();
-    const uint32_t n_chunks = w.n_chunks;
-    // -- chunks round-robin over the warps.  A warp's chunk index only grows, so its slot is found by
-    //    advancing a cursor (warp-uniform; amortised O(1)) instead of searching the table every time.
-    int s = 0;
-    for (uint32_t ch = warp; ch < n_chunks; ch += PRE_THREADS / 32) {
-        while (w.chunk_prefix[s + 1] <= ch) ++s;
-        const int t = (int)(ch - w.chunk_prefix[s]) * 32 + lane;
-        const int sn = w.n[s], srw = w.rw[s];
-        const bool valid = t < sn;
-        const int ty = (valid ? t / srw : 0) + w.y0[s], tx = (valid ? t % srw : 0) + w.x0[s];
-        const bool ok = valid && tile_max_power(w.cox[s], w.coy[s], w.coz[s], w.mx[s], w.my[s], tx, ty) <= w.thr[s];
-        const uint32_t acc = __ballot_sync(FULL, ok);
-        if (acc) {
-            uint32_t start = 0;
-            if (lane == 0) start = atomicAdd(&w.cursor[s], (uint32_t)__popc(acc));
-            if (EMIT) {
-                start = __shfl_sync(FULL, start, 0);
-                if (ok) {
-                    const uint32_t pos = w.off[s] + start + __popc(acc & ((1u << lane) - 1u));
-                    keys[pos] = (uint32_t)(ty * grid_x + tx);
-                    vals[pos] = w.idx[s];
-                }
+    const uint32_t n_rows = w.n_rows;
+    // -- 32 rect rows per warp step, round-robin over the warps
+    for (uint32_t rb = warp * 32; rb < n_rows; rb += PRE_THREADS) {
+        const uint32_t item = rb + lane;
+        const bool valid = item < n_rows;
+        int s = 0;
+        if (valid) {                               // last slot with row_prefix[s] <= item (<= 8 probes)
+            int lo = 0, hi = (int)total_big - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (w.row_prefix[mid] <= item) lo = mid; else hi = mid - 1;
+            }
+            s = lo;
+        }
+        int xa = 1, xb = 0, ty = 0;
+        if (valid) {
+            ty = w.y0[s] + (int)(item - w.row_prefix[s]);
+            row_span(w.cox[s], w.coy[s], w.coz[s], w.mx[s], w.my[s], w.thr[s], ty, w.x0[s], w.x0[s] + w.rw[s], xa, xb);
+        }
+        const uint32_t cnt = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+        // rows of one Gaussian sit in consecutive lanes: segmented (by slot) inclusive scan, one atomic per segment
+        const int key = valid ? s : -1;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            const int k = __shfl_up_sync(FULL, key, o);
+            if (lane >= o && k == key) incl += t;
+        }
+        const int next_key = __shfl_down_sync(FULL, key, 1);
+        const bool seg_last = valid && (lane == 31 || next_key != key);
+        uint32_t seg_base = 0;
+        if (seg_last && incl) seg_base = atomicAdd(&w.cursor[s], incl);
+        if (EMIT) {
+            // broadcast the segment's base from its last lane to the whole segment
+            const uint32_t lastmask = __ballot_sync(FULL, seg_last);
+            const uint32_t ahead = lastmask & ~((1u << lane) - 1u);          // segment ends at or after this lane
+            const int src = ahead ? (__ffs(ahead) - 1) : lane;
+            const uint32_t basev = __shfl_sync(FULL, seg_base, src);
+            if (cnt) {
+                uint32_t pos = w.off[s] + basev + (incl - cnt);
+                const uint32_t gi = w.idx[s];
+                const uint32_t t0 = (uint32_t)(ty * grid_x);
+                for (int x = xa; x <= xb; ++x, ++pos) { keys[pos] = t0 + (uint32_t)x; vals[pos] = gi; }
             }
         }
     }

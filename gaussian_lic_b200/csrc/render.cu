@@ -356,22 +356,22 @@ render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr
                             const float g0 = cv.x, g1 = cv.y, g2 = cv.z;
                             const float one_m = fsub(1.0f, alpha);
                             const float dchannel_dcolor = alpha * T;
-                            const float alpha_inverse = __fdividef(1.0f, one_m);   // MUFU.RCP (gradients are tolerance-pinned)
+                            float alpha_inverse;                                  // 1/(1-alpha), 1-alpha in [0.01, 1]: MUFU.RCP
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(alpha_inverse) : "f"(one_m));
                             float dL_dalpha;
                             ar0 += dchannel_dcolor * c0; acc_c0 += dchannel_dcolor * g0; dL_dalpha = ((c0 * T) + alpha_inverse * ar0) * g0;
                             ar1 += dchannel_dcolor * c1; acc_c1 += dchannel_dcolor * g1; dL_dalpha += ((c1 * T) + alpha_inverse * ar1) * g1;
                             ar2 += dchannel_dcolor * c2; acc_c2 += dchannel_dcolor * g2; dL_dalpha += ((c2 * T) + alpha_inverse * ar2) * g2;
                             T = fmul(T, one_m);
-                            const float dL_dG = op * dL_dalpha;
-                            const float gdx = G * dx, gdy = G * dy;
-                            const float dG_ddelx = -gdx * cx - gdy * cy;
-                            const float dG_ddely = -gdy * cz - gdx * cy;
-                            acc_mx += dL_dG * dG_ddelx * ddelx_dx;
-                            acc_my += dL_dG * dG_ddely * ddely_dy;
-                            acc_cx += -0.5f * gdx * dx * dL_dG;
-                            acc_cy += -0.5f * gdx * dy * dL_dG;
-                            acc_cw += -0.5f * gdy * dy * dL_dG;
-                            acc_o += G * dL_dalpha;
+                            // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per bucket at the flush below
+                            const float gdl = G * dL_dalpha;                      // = dL_dG / opacity
+                            const float gdx = gdl * dx, gdy = gdl * dy;
+                            acc_mx += gdx * cx + gdy * cy;                        // -> * (-opacity * 0.5 * W)
+                            acc_my += gdy * cz + gdx * cy;                        // -> * (-opacity * 0.5 * H)
+                            acc_cx += gdx * dx;                                   // -> * (-0.5 * opacity)
+                            acc_cy += gdx * dy;
+                            acc_cw += gdy * dy;
+                            acc_o += gdl;
                         }
                     }
                 }
@@ -381,11 +381,12 @@ render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr
             if (pfx == x_wrap) { pfx -= (float)TILE; pfy += 1.0f; }
         }
         if (valid_splat) {
-            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx);
-            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my);
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx);
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy);
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw);
+            const float mh = -0.5f * op;
+            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx * (-op * ddelx_dx));
+            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my * (-op * ddely_dy));
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx * mh);
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy * mh);
+            atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw * mh);
             atomicAdd(&dL_dopacity[gid], acc_o);
             atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], acc_c0);
             atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], acc_c1);
