@@ -175,8 +175,8 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
         { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs32(R, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
         if (cur < 0) return cur;
     }
-    const unsigned int flag = (unsigned int)cur;
-    GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(&bin.hdr->sorted_in_b, cur, 1, s));       // 0/1 in the low byte (header is zero-padded)
+    GLIC_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char*>(&bin.hdr->sorted_in_b) + 1, 0, 3, s));
     { StageTimer _t(GLIC_STAGE_RANGES, s); if (int e = launch_tile_ranges(R, nullptr, bin.keys[cur], T, img, !no_color, s)) return e; }
     { StageTimer _t(GLIC_STAGE_RENDER_FWD, s); if (int e = launch_render_forward(vp, no_color != 0, bin.vals[cur], g, img, smp, out_color, out_final_T, s)) return e; }
     if (num_buckets_host) {
@@ -245,8 +245,8 @@ int glic_forward(int P, int sh_degree, int M, const float* means3D, const float*
       const int bit = (int)higher_msb((uint32_t)T);
       cur = launch_sort_pairs32(cap, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s, &g.hdr->r_eff);
       if (cur < 0) return cur; }
-    const unsigned int flag = (unsigned int)cur;
-    GLIC_CUDA_TRY(cudaMemcpyAsync(&bin.hdr->sorted_in_b, &flag, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(&bin.hdr->sorted_in_b, cur, 1, s));       // 0/1 in the low byte (header is zero-padded)
+    GLIC_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char*>(&bin.hdr->sorted_in_b) + 1, 0, 3, s));
     { StageTimer _t(GLIC_STAGE_RANGES, s);
       if (int e = launch_tile_ranges(cap, g.hdr, bin.keys[cur], T, img, !no_color, s)) return e; }
     { StageTimer _t(GLIC_STAGE_RENDER_FWD, s);

@@ -192,6 +192,7 @@ class CRasterizer:
         self.P = 0
         self.cap = 0            # capacity (pairs) the binning / sample workspaces are carved with
         self.cap_target = 0
+        self.stream = None      # cudaStream_t handle (int) or None = legacy default stream
         self.counters = torch.zeros(3, dtype=torch.int64).pin_memory() if torch.cuda.is_available() else torch.zeros(3, dtype=torch.int64)
         self._view_keep = None
 
@@ -238,7 +239,7 @@ class CRasterizer:
                 capi.ptr(radii), capi.ptr(self.geom_ws), self.geom_ws.numel(), capi.ptr(self.image_ws),
                 self.image_ws.numel(), capi.ptr(self.binning_ws), self.binning_ws.numel(),
                 None if no_color else capi.ptr(self.sample_ws), self.sample_ws.numel(), capi.ptr(out_color), capi.ptr(out_T),
-                capi.ptr(self.counters), None), "forward")
+                capi.ptr(self.counters), self.stream), "forward")
             if not sync:
                 break
             if not self.finish():
@@ -274,7 +275,7 @@ class CRasterizer:
             capi.ptr(dL_dpix), lambda_erank, capi.ptr(grads["dL_dmeans2D"]), capi.ptr(grads["dL_dconic"]),
             capi.ptr(grads["dL_dopacity"]), capi.ptr(grads["dL_dcolors"]), capi.ptr(grads["dL_dmeans3D"]),
             capi.ptr(grads["dL_dcov3D"]), capi.ptr(grads["dL_ddc"]), capi.ptr(grads["dL_dsh"]) if self.M else None,
-            capi.ptr(grads["dL_dscales"]), capi.ptr(grads["dL_drots"]), None), "backward")
+            capi.ptr(grads["dL_dscales"]), capi.ptr(grads["dL_drots"]), self.stream), "backward")
         return grads
 
     def loss(self, img, gt, lambda_dssim=0.2, loss_out=None, dL_dimg=None):
@@ -283,7 +284,7 @@ class CRasterizer:
         dL_dimg = torch.empty_like(img) if dL_dimg is None else dL_dimg
         capi.check(self.lib.glic_l1_ssim_loss(3, self.H, self.W, lambda_dssim, capi.ptr(img), capi.ptr(gt),
                                               capi.ptr(loss_out), capi.ptr(dL_dimg), capi.ptr(self.loss_scratch),
-                                              self.loss_scratch.numel(), None), "l1_ssim_loss")
+                                              self.loss_scratch.numel(), self.stream), "l1_ssim_loss")
         return loss_out, dL_dimg
 
     # ---- introspection for parity tests -------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // reference's opaque byte arenas with the reference's own `fromChunk` carvers so
 // tests can compare tile lists / ranges bit-for-bit.
 #include <torch/extension.h>
+#include <memory>
 #include <tuple>
 #include <vector>
 
@@ -97,6 +98,26 @@ std::vector<Tensor> autograd_rasterize(
     return {std::get<0>(r), std::get<1>(r), std::get<2>(r)};
 }
 
+// One step of the reference's SparseGaussianAdam over `params` (each with .grad set), like gaussian.cpp:399-424,703-707.
+// The optimiser object is kept alive across calls (Adam state is keyed by TensorImpl*).
+void sparse_adam_step(std::vector<Tensor> params, std::vector<double> lrs, Tensor visible, int64_t N) {
+    static std::unique_ptr<SparseGaussianAdam> opt;
+    static std::vector<void*> owners;
+    std::vector<void*> now;
+    for (auto& p : params) now.push_back(p.unsafeGetTensorImpl());
+    if (!opt || now != owners) {
+        for (size_t i = 0; i < params.size(); ++i) {
+            std::vector<Tensor> one{params[i]};
+            if (i == 0) opt.reset(new SparseGaussianAdam(one, 0.0, 1e-15));
+            else opt->add_param_group(one);
+            opt->param_groups()[i].options().set_lr(lrs[i]);
+        }
+        owners = now;
+    }
+    opt->set_visibility_and_N(visible, N);
+    opt->step();
+}
+
 Tensor fused_ssim_autograd(Tensor img1, Tensor img2) { return loss_utils::fused_ssim(img1, img2); }
 Tensor l1_autograd(Tensor a, Tensor b) { return loss_utils::l1_loss(a, b); }
 
@@ -112,6 +133,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("autograd_rasterize", &autograd_rasterize);
     m.def("fused_ssim_autograd", &fused_ssim_autograd);
     m.def("l1_autograd", &l1_autograd);
+    m.def("sparse_adam_step", &sparse_adam_step);
     m.def("slice_geom", &slice_geom);
     m.def("slice_binning", &slice_binning);
     m.def("slice_image", &slice_image);
