@@ -155,7 +155,10 @@ def run_ours(args):
     cfg = args.config
     P, W, H, fx, fy, cx, cy, deg, zmax = syn.CONFIGS[cfg]
     g, _ = syn.make_scene(cfg)
-    R_wc, t_wc = syn.orbit_pose(rank % 8)                  # one training view per rank
+    # one training view per rank: an 8-view ring of nearby keyframes around view 0, as a sliding-window
+    # mapper would batch them; the small radius keeps the per-GPU work of the weak-scaling run within a few percent
+    view_id = (rank % 8) if args.view is None else args.view
+    R_wc, t_wc = syn.orbit_pose(view_id, radius=args.rig_radius)
     cam = syn.make_camera(W, H, fx, fy, cx, cy, R_wc, t_wc)
     gt_host = torch.as_tensor(syn.make_gt_image(W, H)).pin_memory()
     gd = ops.scene_to_device(g, dev)
@@ -172,7 +175,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         from gaussian_lic_b200 import dist as gdist
-        allreduce = gdist.GradAllReduce(P, M, dev)
+        # the exchange step: our own two-shot all-reduce over NVLink peer memory (csrc/p2p.cu); --exchange nccl keeps
+        # the library collective as the comparison
+        allreduce = (gdist.P2PGradAllReduce if args.exchange == "p2p" else gdist.GradAllReduce)(P, M, dev)
         grads = allreduce.grads                           # backward writes straight into the collective's buffer
 
     def step():
@@ -193,7 +198,7 @@ def run_ours(args):
     # CUDA-graph the step when it has no collective: forward, loss and backward contain no host synchronisation
     # (capacity-sized binning), so ~25 launches + memsets replay as one graph launch.
     graph = None
-    if allreduce is None and not args.no_graph:
+    if (allreduce is None or args.exchange == "p2p") and not args.no_graph:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -320,6 +325,9 @@ def run_ours(args):
     lrs = dict(means=1.6e-4, dc=2.5e-3, sh=2.5e-3 / 20.0, op=0.05, log_s=0.005, rot=0.001)      # config/fastlivo.yaml:18-22
     opt = ops.SparseGaussianAdam([(params[k], lrs[k]) for k in ("means", "dc", "sh", "op", "log_s", "rot")])
 
+    _PACK = (("means", "dL_dmeans3D"), ("log_s", "dL_dscales"), ("rot", "dL_drots"), ("op", "dL_dopacity"),
+             ("dc", "dL_ddc"), ("sh", "dL_dsh"))
+
     def mapping_iter():
         with torch.cuda.stream(copy_stream):
             gt_d = gt_host.to(dev, non_blocking=True)
@@ -335,7 +343,14 @@ def run_ours(args):
         loss = (1.0 - LAMBDA_DSSIM) * ops.l1_loss(col, gt_d) + LAMBDA_DSSIM * (1.0 - ops.fused_ssim(col.unsqueeze(0), gt_d.unsqueeze(0)))
         loss.backward()
         visible = rad > 0
-        if world > 1:                                                    # mean of per-view gradients, union of visibility
+        if world > 1 and args.exchange == "p2p":                         # mean of per-view gradients, union of visibility
+            for k_, n_ in _PACK:
+                allreduce.grads[n_].view_as(params[k_].grad).copy_(params[k_].grad)
+            _, vis8 = allreduce(rad)
+            for k_, n_ in _PACK:
+                params[k_].grad = allreduce.grads[n_].view_as(params[k_])
+            visible = vis8.view(torch.bool)
+        elif world > 1:
             vis8 = visible.to(torch.uint8)
             works = [dist.all_reduce(p_.grad, async_op=True) for p_ in params.values()]
             works.append(dist.all_reduce(vis8, op=dist.ReduceOp.MAX, async_op=True))
@@ -362,7 +377,7 @@ def run_ours(args):
     map_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
     mapping = {"ms_per_iter": round(map_ms, 4), "views_per_iter": world,
                "what": "H2D image + render + L1/fused-SSIM loss + backward%s + SparseGaussianAdam (6 groups), LibTorch-shim symbols via autograd"
-                       % (" + NCCL all-reduce of grads" if world > 1 else "")}
+                       % ((" + %s all-reduce of grads" % ("NVLink-P2P (own kernels)" if args.exchange == "p2p" else "NCCL")) if world > 1 else "")}
 
     if rank != 0:
         return
@@ -373,7 +388,7 @@ def run_ours(args):
            "config": {"workload": "%s: %d Gaussians, %dx%d, SH degree %d, forward + fused L1/D-SSIM loss + backward, "
                                   "1 view per GPU" % (cfg, P, W, H, deg),
                       "P": P, "V": V, "R": Rn, "B": Bn, "views_per_gpu": 1,
-                      "parallelism": "dp%d (view-sharded%s)" % (world, ", NCCL all-reduce of packed grads" if world > 1 else ""),
+                      "parallelism": "dp%d (view-sharded%s)" % (world, (", in-place all-reduce of packed grads: %s" % ("own NVLink-P2P kernels" if args.exchange == "p2p" else "NCCL")) if world > 1 else ""),
                       "l2": "per-step working set ~%.1f GB > 126 MB L2 (no explicit flush)" % (A1 / 1e9),
                       "cuda_graph": graph is not None},
            "clocks": clocks, "e2e": e2e, "mapping_iter": mapping, "gpu_launches": int(launches), "roofline": roofline,
@@ -502,6 +517,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="Gaussians in the bounded CPU-baseline sample")
+    ap.add_argument("--view", type=int, default=None, help="view of the 8-view rig to render (default: rank % 8)")
+    ap.add_argument("--rig-radius", type=float, default=0.25, help="radius [m] of the multi-view rig")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 gradient exchange: own NVLink peer-memory all-reduce (default) or the NCCL library call")
     ap.add_argument("--no-graph", action="store_true", help="do not CUDA-graph the resident-input step")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (for ncu captures; not a bench value)")
     args = ap.parse_args()

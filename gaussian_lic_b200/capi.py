@@ -58,6 +58,12 @@ def _load():
         "glic_fused_ssim_backward": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_l1_ssim_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
         "glic_knn_mean_dist2": (i32, [i32, vp, vp, vp, sz, vp]),
+        "glic_p2p_buffer_bytes": (sz, [sz, sz]),
+        "glic_p2p_alloc": (i32, [sz, C.POINTER(vp), C.c_char_p]),
+        "glic_p2p_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "glic_p2p_close": (i32, [vp]),
+        "glic_p2p_free": (i32, [vp]),
+        "glic_p2p_allreduce_mean": (i32, [i32, i32, C.POINTER(vp), sz, sz, vp]),
         "glic_debug_geom": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_debug_binning": (i32, [i32, vp, i64, i64, vp, vp, vp, vp]),
         "glic_debug_image": (i32, [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp]),
@@ -87,7 +93,7 @@ def launch_count():
 
 
 STAGES = ["preprocess", "emit", "sort", "ranges", "render_fwd", "loss_fwd", "loss_bwd", "render_bwd", "preprocess_bwd",
-          "adam", "zero"]
+          "adam", "zero", "allreduce"]
 
 
 def profile_enable(on=True):

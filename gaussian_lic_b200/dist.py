@@ -6,8 +6,9 @@ step is a SUM all-reduce of the per-Gaussian gradients (59 floats / Gaussian at 
 all-reduce of the 1-byte visibility mask, after which every replica applies the identical masked Adam
 step (identical inputs -> bit-identical replicas).  The gradient tensors handed to glic_backward are
 views into ONE planar buffer, so the collective runs in place on exactly the bytes the backward kernels
-wrote: no pack / unpack copy.  torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests)
-is the plumbing.
+wrote: no pack / unpack copy.  GradAllReduce runs it through torch.distributed (gloo in the CPU
+tests, NCCL as the library baseline); P2PGradAllReduce is the product path on the GPU box: our own kernels
+over NVLink peer memory.
 """
 import torch
 import torch.distributed as dist
@@ -20,10 +21,11 @@ _LAYOUT = [("dL_drots", 4, (4,)), ("dL_dmeans3D", 3, (3,)), ("dL_dscales", 3, (3
 class PackedGrads:
     """Planar [59*P] gradient buffer + scratch outputs of glic_backward that are not optimiser inputs."""
 
-    def __init__(self, P, M, device):
+    def __init__(self, P, M, device, flat=None, visible=None):
         self.P, self.M = int(P), int(M)
         per = 4 + 3 + 3 + 1 + 3 + 3 * self.M
-        self.flat = torch.zeros(self.P * per, dtype=torch.float32, device=device)
+        self.flat = torch.zeros(self.P * per, dtype=torch.float32, device=device) if flat is None else flat
+        assert self.flat.numel() == self.P * per
         self.grads, off = {}, 0
         for name, k, shape in _LAYOUT:
             if name == "dL_dsh":
@@ -34,7 +36,11 @@ class PackedGrads:
         f32 = dict(dtype=torch.float32, device=device)
         for name, k in (("dL_dmeans2D", 3), ("dL_dconic", 4), ("dL_dcolors", 3), ("dL_dcov3D", 6)):
             self.grads[name] = torch.empty(self.P, k, **f32)
-        self.visible = torch.zeros(self.P, dtype=torch.uint8, device=device)
+        self.visible = torch.zeros(self.P, dtype=torch.uint8, device=device) if visible is None else visible
+
+    @staticmethod
+    def floats_per_gaussian(M):
+        return 4 + 3 + 3 + 1 + 3 + 3 * int(M)
 
     def payload_bytes(self):
         return self.flat.numel() * 4 + self.visible.numel()
@@ -60,6 +66,83 @@ class GradAllReduce:
             dist.all_reduce(pk.visible, op=dist.ReduceOp.MAX, group=self.group)
             pk.flat.mul_(1.0 / self.world)
         return pk.grads, pk.visible
+
+
+class _DevMem:
+    """Raw device allocation exposed through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class P2PGradAllReduce:
+    """Same contract as GradAllReduce, but the exchange is our own two-shot all-reduce over NVLink peer memory
+    (csrc/p2p.cu, glic_p2p_allreduce_mean): every rank's gradient buffer is one cudaMalloc block mapped into all
+    peers through CUDA IPC; torch.distributed only carries the 64-byte handles at construction time.  The call
+    enqueues three kernels on the current stream, never synchronises the host, and is CUDA-graph capturable."""
+
+    def __init__(self, P, M, device, group=None):
+        import ctypes as C
+        from . import capi
+        self._C, self._capi = C, capi
+        self.lib = capi.lib
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise ValueError("P2PGradAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        self.n_floats = int(P) * PackedGrads.floats_per_gaussian(M)
+        self.n_vis = int(P)
+        nbytes = int(self.lib.glic_p2p_buffer_bytes(self.n_floats, self.n_vis))
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        capi.check(self.lib.glic_p2p_alloc(nbytes, C.byref(own), handle), "glic_p2p_alloc")
+        self._own = own.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+        else:
+            handles[0] = handle.raw
+        self._peers = (C.c_void_p * self.world)()
+        for q in range(self.world):
+            if q == self.rank:
+                self._peers[q] = self._own
+            else:
+                peer = C.c_void_p()
+                capi.check(self.lib.glic_p2p_open(handles[q], C.byref(peer)), "glic_p2p_open")
+                self._peers[q] = peer.value
+        raw = torch.as_tensor(_DevMem(self._own, nbytes), device=device)
+        self._raw = raw
+        f_bytes = (self.n_floats * 4 + 255) // 256 * 256
+        flat = raw[:self.n_floats * 4].view(torch.float32)
+        visible = raw[f_bytes:f_bytes + self.n_vis]
+        self.packed = PackedGrads(P, M, device, flat=flat, visible=visible)
+        if self.world > 1:
+            dist.barrier(group=group)            # every peer has mapped every buffer before first use
+
+    @property
+    def grads(self):
+        return self.packed.grads
+
+    def __call__(self, radii):
+        pk = self.packed
+        torch.gt(radii[:pk.P], 0, out=pk.visible.view(torch.bool))
+        stream = torch.cuda.current_stream().cuda_stream
+        self._capi.check(self.lib.glic_p2p_allreduce_mean(self.rank, self.world, self._peers, self.n_floats, self.n_vis,
+                                                          self._C.c_void_p(stream)), "glic_p2p_allreduce_mean")
+        return pk.grads, pk.visible
+
+    def close(self):
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for q in range(self.world):
+            if q != self.rank:
+                self.lib.glic_p2p_close(self._C.c_void_p(self._peers[q]))
+        self.lib.glic_p2p_free(self._C.c_void_p(self._own))
+        self._own = None
 
 
 def shard_views(n_views, rank, world):

@@ -206,6 +206,23 @@ GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint3
                      uint32_t* n_contrib, uint32_t* max_contrib, int64_t* counters2_host /* {R,B}, HOST pointer */, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-GPU exchange step (no counterpart in the reference, which is single-GPU): in-place MEAN all-reduce of the
+ * packed per-Gaussian gradients + OR of the visibility bytes, done by our own kernels over NVLink peer memory
+ * (CUDA IPC mappings of every rank's buffer; two-shot: rank r reduces slice r from all peers and writes it back
+ * to all peers).  Buffer layout: n_floats fp32 | n_vis_bytes bytes | flag words, each part padded to 256 B
+ * (glic_p2p_buffer_bytes).  Every rank must make the same sequence of calls (the barrier epoch is kept on the device,
+ * so the call is CUDA-graph capturable).
+ * glic_p2p_alloc is the one place this library allocates device memory: IPC needs a dedicated cudaMalloc block.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_p2p_buffer_bytes(size_t n_floats, size_t n_vis_bytes);
+GLIC_API int glic_p2p_alloc(size_t bytes, void** dev_ptr_host, unsigned char* handle64_host);
+GLIC_API int glic_p2p_open(const unsigned char* handle64_host, void** peer_ptr_host);
+GLIC_API int glic_p2p_close(void* peer_ptr);
+GLIC_API int glic_p2p_free(void* dev_ptr);
+GLIC_API int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t n_floats, size_t n_vis_bytes,
+                                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stage timing (cudaEvent pairs recorded on the launching stream around each stage; off by
  * default).  glic_profile_enable(1) starts recording and resets the accumulators;
  * glic_profile_read() synchronises the recorded events and returns, per stage, the summed
@@ -214,7 +231,7 @@ GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint3
 enum {
     GLIC_STAGE_PREPROCESS = 0, GLIC_STAGE_EMIT = 1, GLIC_STAGE_SORT = 2, GLIC_STAGE_RANGES = 3,
     GLIC_STAGE_RENDER_FWD = 4, GLIC_STAGE_LOSS_FWD = 5, GLIC_STAGE_LOSS_BWD = 6, GLIC_STAGE_RENDER_BWD = 7,
-    GLIC_STAGE_PREPROCESS_BWD = 8, GLIC_STAGE_ADAM = 9, GLIC_STAGE_ZERO = 10, GLIC_STAGE_COUNT = 11
+    GLIC_STAGE_PREPROCESS_BWD = 8, GLIC_STAGE_ADAM = 9, GLIC_STAGE_ZERO = 10, GLIC_STAGE_ALLREDUCE = 11, GLIC_STAGE_COUNT = 12
 };
 GLIC_API int glic_profile_enable(int on);
 GLIC_API int glic_profile_read(float* ms_host /*[GLIC_STAGE_COUNT]*/, int* count_host /*[GLIC_STAGE_COUNT]*/);
