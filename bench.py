@@ -110,6 +110,7 @@ def cpu_baseline(cfg, sample_P, threads_note=True):
     from gaussian_lic_b200 import synthetic as syn
     from oracle.oracle import Oracle
     o = Oracle(np.float32)
+    o.set_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1; use the host cores we have
     g, cam = syn.make_scene(cfg, P=sample_P)
     gt = syn.make_gt_image(cam["W"], cam["H"])
     t0 = time.perf_counter()

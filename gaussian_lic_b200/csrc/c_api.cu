@@ -130,15 +130,25 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     { StageTimer _t(GLIC_STAGE_PREPROCESS, s);
     if (int e = launch_preprocess_forward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, opacities, dc, sh, vp,
                                           no_color != 0, radii, g, s)) return e; }
+    // R is complete as soon as the preprocess kernel is: ship it to pinned host memory NOW and keep the GPU busy with the
+    // depth sort while the host waits for exactly that copy (the reference blocks here too, rasterizer_impl.cu:398, but
+    // with an idle GPU).
+    static thread_local unsigned int* r_pinned = nullptr;
+    static thread_local cudaEvent_t r_event = nullptr;
+    if (!r_pinned) {
+        GLIC_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&r_pinned), sizeof(unsigned int), cudaHostAllocDefault));
+        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&r_event, cudaEventDisableTiming));
+    }
+    GLIC_CUDA_TRY(cudaMemcpyAsync(r_pinned, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    GLIC_CUDA_TRY(cudaEventRecord(r_event, s));
     {   // depth-first binning: order the Gaussians by (depth, index) once, then prefix-sum their tile counts in that order
         StageTimer _t(GLIC_STAGE_SORT, s);
         const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
         if (cur < 0) return cur;
         if (int e = launch_depth_scan(P, g, g.order[cur], 0xFFFFFFFFll, s)) return e;
     }
-    unsigned int total = 0;
-    GLIC_CUDA_TRY(cudaMemcpyAsync(&total, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-    GLIC_CUDA_TRY(cudaStreamSynchronize(s));
+    GLIC_CUDA_TRY(cudaEventSynchronize(r_event));
+    const unsigned int total = *r_pinned;
     *num_rendered_host = (int64_t)total;
     return GLIC_OK;
 }

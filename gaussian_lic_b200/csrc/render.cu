@@ -254,30 +254,52 @@ live_scan_kernel(int T, const uint32_t* __restrict__ max_contrib, uint32_t* __re
     if (tid == 0) hdr->num_live_buckets = carry;
 }
 
-constexpr int BWD_WARPS = 8;
+constexpr int BWD_WARPS = 4;              // warps per CTA; every warp owns one live bucket at a time
+constexpr int BWD_ROWPAIRS = TILE / 2;    // a lane owns one pixel in each of the 8 row pairs of the tile
 
-__global__ void __launch_bounds__(BWD_WARPS * 32)
-render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
+// Backward of the blend, pixel-major inside a 32-splat bucket (replaces PerGaussianRenderCUDA, backward.cu:400-597).
+//
+// One warp per LIVE bucket (persistent grid-stride loop), lane l owns the 8 pixels (column l & 15, rows 2j + (l >> 4)) of
+// the 16x16 tile.  Every pixel restarts from the bucket's checkpoint (T, C) and walks the bucket's splats in list order
+// exactly like the forward, so T and the colour prefix need no hand-over between lanes and the eight pixels of a lane
+// are eight independent dependency chains.  A (splat, row pair) is visited only if the splat's alpha >= 1/255 ellipse can
+// reach those rows (the forward's conservative half-extent test => skipped pairs contribute exactly zero) and some pixel
+// of the pair got this far.  The nine per-splat sums are accumulated over the lane's pixels in registers, combined across
+// the warp by one reduce-scatter (8 values in 3 halving exchanges + 2 butterflies; the 9th by butterfly) and leave as
+// 9 RED per splat and bucket -- the same global-atomic count as the reference's per-splat formulation, without its
+// 287-step shuffle pipeline (4 shuffles + bookkeeping per pixel-splat pair).
+__global__ void __launch_bounds__(BWD_WARPS * 32, 4)
+render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
                        const uint32_t* __restrict__ bucket_offsets, const uint32_t* __restrict__ live_offsets,
                        const float4* __restrict__ ckpt, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ pixel_colors, const float* __restrict__ dL_dpix,
                        float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
                        float* __restrict__ dL_dcolors) {
-    // per warp: two 32-pixel groups (ring) of {T, C-Cfinal} state and {dL/dC, n_contrib} constants
-    __shared__ float4 s_state[BWD_WARPS][32];
-    __shared__ float4 s_const[BWD_WARPS][64];
+    __shared__ float4 s_sp[BWD_WARPS][BUCKET][3];            // the bucket's splat records, per warp
+    __shared__ uint32_t s_gid[BWD_WARPS][BUCKET];
+    __shared__ uint32_t s_rows[BWD_WARPS][BUCKET];           // row pairs each splat can reach (8-bit mask)
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_live = hdr->num_live_buckets;
     const uint32_t warps_total = gridDim.x * BWD_WARPS;
     const size_t HW = (size_t)vp.W * vp.H;
     const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
-    float4* st = s_state[warp];
-    float4* cs = s_const[warp];
+    float4 (*sp)[3] = s_sp[warp];
+
+    // destination of this lane's reduce-scatter result: value slot v = lane >> 2 (held by lanes with (lane & 3) == 0)
+    //   slot: 0 mean.x, 1 mean.y, 2 conic.x, 3 conic.y, 4 conic.w, 5..7 colour; lane 1 additionally carries opacity
+    const int slot = lane >> 2;
+    float* dst_base; int dst_stride, dst_off; float f_op, f_one;
+    if (lane == 1) { dst_base = dL_dopacity; dst_stride = 1; dst_off = 0; f_op = 0.f; f_one = 1.f; }
+    else if (slot < 2) { dst_base = dL_dmean2D; dst_stride = 3; dst_off = slot; f_op = slot == 0 ? -ddelx_dx : -ddely_dy; f_one = 0.f; }
+    else if (slot < 5) { dst_base = dL_dconic; dst_stride = 4; dst_off = slot == 4 ? 3 : slot - 2; f_op = -0.5f; f_one = 0.f; }
+    else { dst_base = dL_dcolors; dst_stride = 3; dst_off = slot - 5; f_op = 0.f; f_one = 1.f; }
+    const bool i_write = (lane & 3) == 0 || lane == 1;
 
     for (uint32_t live = blockIdx.x * BWD_WARPS + warp; live < n_live; live += warps_total) {
         // tile of this live bucket: first t with live_offsets[t] > live -- 32-ary search, one probe per lane
-        int lo = 0, cnt = T;
+        int lo = 0, cnt = T_tiles;
         while (cnt > 1) {
             const int step = (cnt + 31) >> 5;
             const int probe = lo + min((lane + 1) * step, cnt) - 1;              // last tile of this lane's sub-range
@@ -291,108 +313,127 @@ render_backward_kernel(ViewParams vp, int T, const ImageHeader* __restrict__ hdr
         const uint32_t bucket = (tile == 0 ? 0u : bucket_offsets[tile - 1]) + (uint32_t)bucket_in_tile;
         const uint2 range = ranges[tile];
         const int n_splats = (int)(range.y - range.x);
-        const int splat_in_tile = bucket_in_tile * BUCKET + lane;
-        const bool valid_splat = splat_in_tile < n_splats;
-
-        uint32_t gid = 0;
-        float mx = 0.f, my = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        if (valid_splat) {
-            gid = point_list[range.x + splat_in_tile];
-            const float4 r0 = rec[3 * (size_t)gid + 0];
-            const float4 r1 = rec[3 * (size_t)gid + 1];
-            const float4 r2 = rec[3 * (size_t)gid + 2];
-            mx = r0.x; my = r0.y; cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
-        }
+        const int bucket_start = bucket_in_tile * BUCKET;
+        const int n_valid = min(BUCKET, n_splats - bucket_start);
         const int tile_x = tile % vp.grid_x, tile_y = tile / vp.grid_x;
-        const int pix_min_x = tile_x * TILE, pix_min_y = tile_y * TILE;
-        const float4* ck = ckpt + (size_t)bucket * TILE_PIX;
+        const int qx = tile_x * TILE + (lane & (TILE - 1)), qy0 = tile_y * TILE + (lane >> 4);
+        const float pfx = (float)qx;
 
-        float acc_mx = 0.f, acc_my = 0.f, acc_cx = 0.f, acc_cy = 0.f, acc_cw = 0.f, acc_o = 0.f;
-        float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
-        float T = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;
-        // pixel handled by this lane at step i is p = i - lane; track its coordinates incrementally
-        int p = -lane;
-        float pfx = (float)(pix_min_x + ((-lane) & (TILE - 1))), pfy = (float)(pix_min_y) - (float)((lane + TILE - 1) >> 4);
-        const float x_wrap = (float)(pix_min_x + TILE);
+        // this lane's 8 pixels: contributors left inside this bucket (0 = never got here) and restart state
+        int rel[BWD_ROWPAIRS];
+        float Tr[BWD_ROWPAIRS], a0[BWD_ROWPAIRS], a1[BWD_ROWPAIRS], a2[BWD_ROWPAIRS];
+        float g0[BWD_ROWPAIRS], g1[BWD_ROWPAIRS], g2[BWD_ROWPAIRS];
+        uint32_t alive_rows = 0;
+        int n_max = 0;
+#pragma unroll
+        for (int j = 0; j < BWD_ROWPAIRS; ++j) {
+            const int qy = qy0 + 2 * j;
+            int n = 0;
+            size_t qi = 0;
+            if (qx < vp.W && qy < vp.H) { qi = (size_t)qy * vp.W + qx; n = (int)n_contrib[qi]; }
+            rel[j] = min(max(n - bucket_start, 0), BUCKET);
+            Tr[j] = a0[j] = a1[j] = a2[j] = g0[j] = g1[j] = g2[j] = 0.f;
+            if (rel[j] > 0) {
+                const float4 k4 = ckpt[(size_t)bucket * TILE_PIX + j * 32 + lane];
+                Tr[j] = k4.x;
+                a0[j] = k4.y - pixel_colors[qi]; a1[j] = k4.z - pixel_colors[HW + qi]; a2[j] = k4.w - pixel_colors[2 * HW + qi];
+                g0[j] = dL_dpix[qi]; g1[j] = dL_dpix[HW + qi]; g2[j] = dL_dpix[2 * HW + qi];
+            }
+            const int m = (int)__reduce_max_sync(0xffffffffu, (unsigned)rel[j]);
+            if (m > 0) alive_rows |= 1u << j;
+            n_max = max(n_max, m);
+        }
 
-        for (int i = 0; i < TILE_PIX + 31; ++i, ++p) {
-            if ((i & 31) == 0 && i < TILE_PIX) {
-                // coalesced fill of the next 32 pixels: lane l <-> pixel i + l of the tile
-                __syncwarp();
-                const int q = i + lane;
-                const int qx = pix_min_x + (q & (TILE - 1)), qy = pix_min_y + (q >> 4);
-                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (qx < vp.W && qy < vp.H) {
-                    const size_t qi = (size_t)qy * vp.W + qx;
-                    const int n = (int)n_contrib[qi];
-                    if (n > bucket_in_tile * BUCKET) {               // pixel reached this bucket: checkpoint is valid
-                        const float4 k4 = ck[q];
-                        sv = make_float4(k4.x, k4.y - pixel_colors[qi], k4.z - pixel_colors[HW + qi], k4.w - pixel_colors[2 * HW + qi]);
-                        cv = make_float4(dL_dpix[qi], dL_dpix[HW + qi], dL_dpix[2 * HW + qi], __int_as_float(n));
-                    }
+        // stage the bucket's splats (lane l <-> splat l) and the row pairs each one can reach
+        {
+            uint32_t gid = 0;
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+            uint32_t rows = 0;
+            if (lane < n_valid && lane < n_max) {
+                gid = point_list[range.x + bucket_start + lane];
+                r0 = rec[3 * (size_t)gid + 0]; r1 = rec[3 * (size_t)gid + 1]; r2 = rec[3 * (size_t)gid + 2];
+#pragma unroll
+                for (int j = 0; j < BWD_ROWPAIRS; ++j) {
+                    const float row_mid = (float)(tile_y * TILE + 2 * j) + 0.5f;
+                    if (!(fabsf(row_mid - r0.y) > r2.w + 0.5f)) rows |= 1u << j;
                 }
-                st[lane] = sv;
-                cs[(i & 32) + lane] = cv;
-                __syncwarp();
             }
-            // hand the running state to the next splat (lane+1), which treats the same pixel next
-            T = __shfl_up_sync(0xffffffffu, T, 1);
-            ar0 = __shfl_up_sync(0xffffffffu, ar0, 1);
-            ar1 = __shfl_up_sync(0xffffffffu, ar1, 1);
-            ar2 = __shfl_up_sync(0xffffffffu, ar2, 1);
-            if (lane == 0 && i < TILE_PIX) {
-                const float4 sv = st[i & 31];
-                T = sv.x; ar0 = sv.y; ar1 = sv.z; ar2 = sv.w;
-            }
-            if (valid_splat && p >= 0 && p < TILE_PIX) {
-                const float4 cv = cs[p & 63];
-                if (splat_in_tile < __float_as_int(cv.w)) {
-                    const float dx = fsub(mx, pfx), dy = fsub(my, pfy);
-                    const float power = splat_power(dx, dy, cx, cy, cz);
+            __syncwarp();                                    // previous bucket's readers are done
+            sp[lane][0] = r0; sp[lane][1] = r1; sp[lane][2] = r2;
+            s_gid[warp][lane] = gid;
+            s_rows[warp][lane] = rows & alive_rows;
+            __syncwarp();
+        }
+
+        uint32_t todo = __ballot_sync(0xffffffffu, s_rows[warp][lane] != 0);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float4 a = sp[k][0], b = sp[k][1];
+            const float c2 = sp[k][2].x;
+            const uint32_t rows = s_rows[warp][k];
+            const float dx = fsub(a.x, pfx);
+            const float cxdx = fmul(dx, a.z);                // shared by the lane's pixels: same column
+            float v_mx = 0.f, v_my = 0.f, v_cx = 0.f, v_cy = 0.f, v_cw = 0.f, v_c0 = 0.f, v_c1 = 0.f, v_c2 = 0.f, v_o = 0.f;
+#pragma unroll
+            for (int j = 0; j < BWD_ROWPAIRS; ++j) {
+                if (!((rows >> j) & 1u)) continue;           // warp-uniform
+                if (k < rel[j]) {
+                    const float dy = fsub(a.y, (float)(qy0 + 2 * j));
+                    // splat_power(dx, dy, cx, cy, cz) with the dx*cx product hoisted (same operation order)
+                    const float power = fsub(fmul(ffma(dx, cxdx, fmul(dy, fmul(dy, b.x))), -0.5f), fmul(dy, fmul(dx, a.w)));
                     if (power <= 0.0f) {
                         const float G = expf(power);
-                        const float alpha = fminf(0.99f, fmul(op, G));
+                        const float alpha = fminf(0.99f, fmul(b.y, G));
                         if (alpha >= (1.0f / 255.0f)) {
-                            const float g0 = cv.x, g1 = cv.y, g2 = cv.z;
                             const float one_m = fsub(1.0f, alpha);
+                            const float T = Tr[j];
                             const float dchannel_dcolor = alpha * T;
                             float alpha_inverse;                                  // 1/(1-alpha), 1-alpha in [0.01, 1]: MUFU.RCP
                             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(alpha_inverse) : "f"(one_m));
                             float dL_dalpha;
-                            ar0 += dchannel_dcolor * c0; acc_c0 += dchannel_dcolor * g0; dL_dalpha = ((c0 * T) + alpha_inverse * ar0) * g0;
-                            ar1 += dchannel_dcolor * c1; acc_c1 += dchannel_dcolor * g1; dL_dalpha += ((c1 * T) + alpha_inverse * ar1) * g1;
-                            ar2 += dchannel_dcolor * c2; acc_c2 += dchannel_dcolor * g2; dL_dalpha += ((c2 * T) + alpha_inverse * ar2) * g2;
-                            T = fmul(T, one_m);
-                            // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per bucket at the flush below
+                            a0[j] += dchannel_dcolor * b.z; v_c0 += dchannel_dcolor * g0[j]; dL_dalpha = ((b.z * T) + alpha_inverse * a0[j]) * g0[j];
+                            a1[j] += dchannel_dcolor * b.w; v_c1 += dchannel_dcolor * g1[j]; dL_dalpha += ((b.w * T) + alpha_inverse * a1[j]) * g1[j];
+                            a2[j] += dchannel_dcolor * c2; v_c2 += dchannel_dcolor * g2[j]; dL_dalpha += ((c2 * T) + alpha_inverse * a2[j]) * g2[j];
+                            Tr[j] = fmul(T, one_m);
+                            // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per splat below
                             const float gdl = G * dL_dalpha;                      // = dL_dG / opacity
                             const float gdx = gdl * dx, gdy = gdl * dy;
-                            acc_mx += gdx * cx + gdy * cy;                        // -> * (-opacity * 0.5 * W)
-                            acc_my += gdy * cz + gdx * cy;                        // -> * (-opacity * 0.5 * H)
-                            acc_cx += gdx * dx;                                   // -> * (-0.5 * opacity)
-                            acc_cy += gdx * dy;
-                            acc_cw += gdy * dy;
-                            acc_o += gdl;
+                            v_mx += gdx * a.z + gdy * a.w;                        // -> * (-opacity * 0.5 * W)
+                            v_my += gdy * b.x + gdx * a.w;                        // -> * (-opacity * 0.5 * H)
+                            v_cx += gdx * dx;                                     // -> * (-0.5 * opacity)
+                            v_cy += gdx * dy;
+                            v_cw += gdy * dy;
+                            v_o += gdl;
                         }
                     }
                 }
             }
-            // next pixel of this lane (row-major inside the 16x16 tile)
-            pfx += 1.0f;
-            if (pfx == x_wrap) { pfx -= (float)TILE; pfy += 1.0f; }
+            // v_o != 0 iff some pixel of this lane contributed?  gdl can be exactly 0 (zero image gradient): then every
+            // sum of the lane is 0 as well, so skipping is exact.
+            if (!__any_sync(0xffffffffu, v_o != 0.f || v_c0 != 0.f || v_c1 != 0.f || v_c2 != 0.f)) continue;
+            // reduce-scatter of 8 values over the 32 lanes: halve the value set at xor 16, 8, 4, then plain butterflies
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            const float r0 = (h16 ? v_cw : v_mx) + __shfl_xor_sync(0xffffffffu, h16 ? v_mx : v_cw, 16);
+            const float r1 = (h16 ? v_c0 : v_my) + __shfl_xor_sync(0xffffffffu, h16 ? v_my : v_c0, 16);
+            const float r2 = (h16 ? v_c1 : v_cx) + __shfl_xor_sync(0xffffffffu, h16 ? v_cx : v_c1, 16);
+            const float r3 = (h16 ? v_c2 : v_cy) + __shfl_xor_sync(0xffffffffu, h16 ? v_cy : v_c2, 16);
+            const float q0 = (h8 ? r2 : r0) + __shfl_xor_sync(0xffffffffu, h8 ? r0 : r2, 8);
+            const float q1 = (h8 ? r3 : r1) + __shfl_xor_sync(0xffffffffu, h8 ? r1 : r3, 8);
+            float w0 = (h4 ? q1 : q0) + __shfl_xor_sync(0xffffffffu, h4 ? q0 : q1, 4);
+            w0 += __shfl_xor_sync(0xffffffffu, w0, 2);
+            w0 += __shfl_xor_sync(0xffffffffu, w0, 1);
+            v_o += __shfl_xor_sync(0xffffffffu, v_o, 16);
+            v_o += __shfl_xor_sync(0xffffffffu, v_o, 8);
+            v_o += __shfl_xor_sync(0xffffffffu, v_o, 4);
+            v_o += __shfl_xor_sync(0xffffffffu, v_o, 2);
+            v_o += __shfl_xor_sync(0xffffffffu, v_o, 1);
+            if (i_write) {
+                const size_t gid = s_gid[warp][k];
+                const float val = lane == 1 ? v_o : w0;
+                atomicAdd(dst_base + dst_stride * gid + dst_off, val * (f_op * b.y + f_one));
+            }
         }
-        if (valid_splat) {
-            const float mh = -0.5f * op;
-            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], acc_mx * (-op * ddelx_dx));
-            atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], acc_my * (-op * ddely_dy));
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 0], acc_cx * mh);
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 1], acc_cy * mh);
-            atomicAdd(&dL_dconic[4 * (size_t)gid + 3], acc_cw * mh);
-            atomicAdd(&dL_dopacity[gid], acc_o);
-            atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], acc_c0);
-            atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], acc_c1);
-            atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], acc_c2);
-        }
-        __syncwarp();
     }
 }
 

@@ -94,31 +94,24 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
         torch::Tensor shc = M > 0 ? f32c(sh) : torch::Tensor();
         ViewHold vh = make_view(viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, limx_neg, limx_pos, limy_neg, limy_pos, H, W);
         void* st = cur_stream();
-        // Single asynchronous forward: the binning / sample buffers are sized by a capacity remembered from the
-        // previous frame (+12.5 %), so num_rendered never has to reach the host in the middle of the pipeline.
-        // One stream synchronisation at the end delivers the two ints the reference API returns.
-        static int64_t cap_guess = 0;
-        static int64_t* counters = nullptr;                     // pinned {R, B, overflow}
-        if (!counters) TORCH_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&counters), 4 * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess,
-                                   "glic_b200: cudaHostAlloc failed");
-        int64_t cap_target = std::max<int64_t>(cap_guess, (int64_t)8 * P + 65536);
-        for (int attempt = 0; attempt < 4; ++attempt) {
-            binningBuffer = torch::empty({(int64_t)glic_binning_bytes(cap_target)}, bopt);
-            sampleBuffer = no_color ? torch::empty({0}, bopt) : torch::empty({(int64_t)glic_sample_bytes(cap_target, W, H)}, bopt);
-            check(glic_forward(P, degree, M, m.data_ptr<float>(), s.data_ptr<float>(), scale_modifier, r.data_ptr<float>(),
-                               o.data_ptr<float>(), d.data_ptr<float>(), M > 0 ? shc.data_ptr<float>() : nullptr, &vh.view,
-                               no_color ? 1 : 0, radii.data_ptr<int>(), geomBuffer.data_ptr(), (size_t)geomBuffer.numel(),
-                               imgBuffer.data_ptr(), (size_t)imgBuffer.numel(), binningBuffer.data_ptr(),
-                               (size_t)binningBuffer.numel(), no_color ? nullptr : sampleBuffer.data_ptr(),
-                               (size_t)sampleBuffer.numel(), out_color.data_ptr<float>(), out_final_T.data_ptr<float>(), counters, st),
-                  "forward");
-            c10::cuda::getCurrentCUDAStream().synchronize();
-            rendered = counters[0]; buckets = counters[1];
-            if (counters[2] == 0) break;
-            TORCH_CHECK(attempt < 3, "glic_b200: binning capacity did not converge");
-            cap_target = rendered + rendered / 8 + 65536;       // overflow: size for the R just measured and run again
-        }
-        cap_guess = rendered + rendered / 8 + 65536;
+        // Two stages split exactly where the reference reads num_rendered back (rasterizer_impl.cu:398): the host waits
+        // only for the preprocess kernel (R travels to pinned memory while the GPU already sorts by depth), sizes the
+        // binning / sample buffers EXACTLY, enqueues the rest and returns -- the render is still running when the caller
+        // starts enqueuing its loss.  num_buckets would need a second wait (rasterizer_impl.cu:446); the backward here
+        // reads it from the image header on the device, so the int handed back is the analytic upper bound.
+        check(glic_forward_preprocess(P, degree, M, m.data_ptr<float>(), s.data_ptr<float>(), scale_modifier, r.data_ptr<float>(),
+                                      o.data_ptr<float>(), d.data_ptr<float>(), M > 0 ? shc.data_ptr<float>() : nullptr, &vh.view,
+                                      no_color ? 1 : 0, radii.data_ptr<int>(), geomBuffer.data_ptr(), (size_t)geomBuffer.numel(),
+                                      imgBuffer.data_ptr(), (size_t)imgBuffer.numel(), &rendered, st),
+              "forward_preprocess");
+        binningBuffer = torch::empty({(int64_t)glic_binning_bytes(rendered)}, bopt);
+        if (!no_color) sampleBuffer = torch::empty({(int64_t)glic_sample_bytes(rendered, W, H)}, bopt);
+        check(glic_forward_render(P, &vh.view, no_color ? 1 : 0, rendered, geomBuffer.data_ptr(), imgBuffer.data_ptr(),
+                                  binningBuffer.data_ptr(), (size_t)binningBuffer.numel(), no_color ? nullptr : sampleBuffer.data_ptr(),
+                                  (size_t)sampleBuffer.numel(), out_color.data_ptr<float>(), out_final_T.data_ptr<float>(),
+                                  /*num_buckets_host=*/nullptr, st),
+              "forward_render");
+        buckets = no_color ? 0 : glic_max_buckets(rendered, W, H);
     }
     return std::make_tuple((int)rendered, (int)buckets, out_color, out_final_T, radii, geomBuffer, binningBuffer, imgBuffer,
                            sampleBuffer);
@@ -161,9 +154,8 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
         auto rad = radii.contiguous();
         auto gb = geomBuffer.contiguous(), bb = binningBuffer.contiguous(), ib = imageBuffer.contiguous(), sb = sampleBuffer.contiguous();
         ViewHold vh = make_view(viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, limx_neg, limx_pos, limy_neg, limy_pos, H, W);
-        // the workspaces were carved with the CAPACITY derived from their byte sizes (see RasterizeGaussiansCUDA), not with R
-        const int64_t cap = glic_binning_capacity((size_t)bb.numel(), (size_t)sb.numel(), W, H, 0);
-        (void)R;
+        // R is the exact num_rendered the forward carved its workspaces with (ctx round trip, rasterizer.cpp)
+        const int64_t cap = R;
         check(glic_backward(P, degree, M, m.data_ptr<float>(), s.data_ptr<float>(), scale_modifier, r.data_ptr<float>(),
                             d.data_ptr<float>(), M > 0 ? shc.data_ptr<float>() : nullptr, &vh.view, rad.data_ptr<int>(),
                             cap, gb.data_ptr(), bb.data_ptr(), ib.data_ptr(), sb.data_ptr(), g.data_ptr<float>(), lambda_erank,

@@ -42,6 +42,10 @@ class Oracle:
         self.lib.glic_oracle_higher_msb.restype = C.c_uint32
         self.lib.glic_oracle_ranges.restype = C.c_uint32
 
+    def set_threads(self, n):
+        """Override OMP_NUM_THREADS (torchrun exports 1) for the timed CPU legs."""
+        self.lib.glic_oracle_set_threads(C.c_int(int(n)))
+
     def max_threads(self):
         return int(self.lib.glic_oracle_max_threads())
 
