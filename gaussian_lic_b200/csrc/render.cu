@@ -156,16 +156,20 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
         waited = i + 1;
         const SplatRec* batch = s_rec[i & 1];
         const int nb = min(TILE_PIX, n_splats - i * TILE_PIX);
-        if (!done) {
-            for (int j = 0; j < nb; ++j) {
-                if ((j & (BUCKET - 1)) == 0 && !no_color) {           // checkpoint every 32 splats
-                    ckpt[(size_t)bbm * TILE_PIX + tid] = make_float4(T, C0, C1, C2);
-                    ++bbm;
-                }
-                const float4 c = batch[j].c;
-                const float4 a = batch[j].a;
+        // one checkpoint per 32-splat bucket, then the bucket's splats: the bucket loop keeps the checkpoint bookkeeping
+        // out of the per-splat instruction stream
+        for (int jb = 0; jb < nb && !done; jb += BUCKET) {
+            if (!no_color) {
+                ckpt[(size_t)bbm * TILE_PIX + tid] = make_float4(T, C0, C1, C2);
+                ++bbm;
+            }
+            const int je = min(jb + BUCKET, nb);
+            const SplatRec* sr = batch + jb;
+            for (int j = jb; j < je; ++j, ++sr) {
+                const float4 c = sr->c;
+                const float4 a = sr->a;
                 if (fabsf(row_mid - a.y) > c.w + 0.5f) continue;      // warp-uniform row-pair cull
-                const float4 b = batch[j].b;
+                const float4 b = sr->b;
                 const float dx = fsub(a.x, pfx), dy = fsub(a.y, pfy);
                 const float power = splat_power(dx, dy, a.z, a.w, b.x);
                 if (power > 0.0f) continue;
