@@ -121,7 +121,7 @@ struct ImageHeader {
     long long num_rendered;     // R
     unsigned int num_buckets;   // B
     unsigned int num_live_buckets;   // buckets some pixel reached (backward work list)
-    unsigned int pad0;
+    unsigned int bwd_ticket;    // dynamic work counter of the backward's persistent warps (reset by live_scan_kernel)
     long long counters[4];      // {R, B, overflow, 0}: copied to the host asynchronously by glic_forward
     unsigned int pad[20];
 };

@@ -255,16 +255,15 @@ live_scan_kernel(int T, const uint32_t* __restrict__ max_contrib, uint32_t* __re
         if (tid == 1023) carry = out;
         __syncthreads();
     }
-    if (tid == 0) hdr->num_live_buckets = carry;
+    if (tid == 0) { hdr->num_live_buckets = carry; hdr->bwd_ticket = 0; }
 }
 
-constexpr int BWD_WARPS = 4;              // warps per CTA; every warp owns one live bucket at a time
-constexpr int BWD_ROWPAIRS = TILE / 2;    // a lane owns one pixel in each of the 8 row pairs of the tile
+constexpr int BWD_WARPS = 4;              // warps per CTA; every warp owns one (live bucket, tile part) at a time
 
 // Backward of the blend, pixel-major inside a 32-splat bucket (replaces PerGaussianRenderCUDA, backward.cu:400-597).
 //
-// One warp per LIVE bucket (persistent grid-stride loop), lane l owns the 8 pixels (column l & 15, rows 2j + (l >> 4)) of
-// the 16x16 tile.  Every pixel restarts from the bucket's checkpoint (T, C) and walks the bucket's splats in list order
+// One warp per (LIVE bucket, tile part) in a persistent grid-stride loop; a part is RP consecutive row pairs of the 16x16
+// tile (RP = 8: whole tile, RP = 4: half), and lane l owns the RP pixels (column l & 15, rows 2j + (l >> 4)) of its part.  Every pixel restarts from the bucket's checkpoint (T, C) and walks the bucket's splats in list order
 // exactly like the forward, so T and the colour prefix need no hand-over between lanes and the eight pixels of a lane
 // are eight independent dependency chains.  A (splat, row pair) is visited only if the splat's alpha >= 1/255 ellipse can
 // reach those rows (the forward's conservative half-extent test => skipped pairs contribute exactly zero) and some pixel
@@ -272,8 +271,9 @@ constexpr int BWD_ROWPAIRS = TILE / 2;    // a lane owns one pixel in each of th
 // the warp by one reduce-scatter (8 values in 3 halving exchanges + 2 butterflies; the 9th by butterfly) and leave as
 // 9 RED per splat and bucket -- the same global-atomic count as the reference's per-splat formulation, without its
 // 287-step shuffle pipeline (4 shuffles + bookkeeping per pixel-splat pair).
-__global__ void __launch_bounds__(BWD_WARPS * 32, 4)
-render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
+template <int BWD_ROWPAIRS, int GRP, int MIN_CTAS>
+__global__ void __launch_bounds__(BWD_WARPS * 32, MIN_CTAS)
+render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
                        const uint32_t* __restrict__ bucket_offsets, const uint32_t* __restrict__ live_offsets,
                        const float4* __restrict__ ckpt, const uint32_t* __restrict__ n_contrib,
@@ -286,7 +286,6 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_live = hdr->num_live_buckets;
-    const uint32_t warps_total = gridDim.x * BWD_WARPS;
     const size_t HW = (size_t)vp.W * vp.H;
     const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
     float4 (*sp)[3] = s_sp[warp];
@@ -301,7 +300,15 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
     else { dst_base = dL_dcolors; dst_stride = 3; dst_off = slot - 5; f_op = 0.f; f_one = 1.f; }
     const bool i_write = (lane & 3) == 0 || lane == 1;
 
-    for (uint32_t live = blockIdx.x * BWD_WARPS + warp; live < n_live; live += warps_total) {
+    constexpr int PARTS = (TILE / 2) / BWD_ROWPAIRS;
+    // work items are handed out dynamically (one ticket per warp and item): buckets differ by more than 10x in cost
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&hdr->bwd_ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_live * PARTS) break;
+        const uint32_t live = item / PARTS;
+        const int part = (int)(item % PARTS);
         // tile of this live bucket: first t with live_offsets[t] > live -- 32-ary search, one probe per lane
         int lo = 0, cnt = T_tiles;
         while (cnt > 1) {
@@ -320,14 +327,15 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
         const int bucket_start = bucket_in_tile * BUCKET;
         const int n_valid = min(BUCKET, n_splats - bucket_start);
         const int tile_x = tile % vp.grid_x, tile_y = tile / vp.grid_x;
-        const int qx = tile_x * TILE + (lane & (TILE - 1)), qy0 = tile_y * TILE + (lane >> 4);
+        const int row0 = tile_y * TILE + 2 * BWD_ROWPAIRS * part;       // first tile row of this part
+        const int qx = tile_x * TILE + (lane & (TILE - 1)), qy0 = row0 + (lane >> 4);
         const float pfx = (float)qx;
 
         // this lane's 8 pixels: contributors left inside this bucket (0 = never got here) and restart state
         int rel[BWD_ROWPAIRS];
         float Tr[BWD_ROWPAIRS], a0[BWD_ROWPAIRS], a1[BWD_ROWPAIRS], a2[BWD_ROWPAIRS];
         float g0[BWD_ROWPAIRS], g1[BWD_ROWPAIRS], g2[BWD_ROWPAIRS];
-        uint32_t alive_rows = 0;
+        int rel_max[BWD_ROWPAIRS];                            // warp-uniform: deepest pixel of each row pair
         int n_max = 0;
 #pragma unroll
         for (int j = 0; j < BWD_ROWPAIRS; ++j) {
@@ -338,14 +346,13 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
             rel[j] = min(max(n - bucket_start, 0), BUCKET);
             Tr[j] = a0[j] = a1[j] = a2[j] = g0[j] = g1[j] = g2[j] = 0.f;
             if (rel[j] > 0) {
-                const float4 k4 = ckpt[(size_t)bucket * TILE_PIX + j * 32 + lane];
+                const float4 k4 = ckpt[(size_t)bucket * TILE_PIX + (part * BWD_ROWPAIRS + j) * 32 + lane];
                 Tr[j] = k4.x;
                 a0[j] = k4.y - pixel_colors[qi]; a1[j] = k4.z - pixel_colors[HW + qi]; a2[j] = k4.w - pixel_colors[2 * HW + qi];
                 g0[j] = dL_dpix[qi]; g1[j] = dL_dpix[HW + qi]; g2[j] = dL_dpix[2 * HW + qi];
             }
-            const int m = (int)__reduce_max_sync(0xffffffffu, (unsigned)rel[j]);
-            if (m > 0) alive_rows |= 1u << j;
-            n_max = max(n_max, m);
+            rel_max[j] = (int)__reduce_max_sync(0xffffffffu, (unsigned)rel[j]);
+            n_max = max(n_max, rel_max[j]);
         }
 
         // stage the bucket's splats (lane l <-> splat l) and the row pairs each one can reach
@@ -358,14 +365,14 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
                 r0 = rec[3 * (size_t)gid + 0]; r1 = rec[3 * (size_t)gid + 1]; r2 = rec[3 * (size_t)gid + 2];
 #pragma unroll
                 for (int j = 0; j < BWD_ROWPAIRS; ++j) {
-                    const float row_mid = (float)(tile_y * TILE + 2 * j) + 0.5f;
-                    if (!(fabsf(row_mid - r0.y) > r2.w + 0.5f)) rows |= 1u << j;
+                    const float row_mid = (float)(row0 + 2 * j) + 0.5f;
+                    if (lane < rel_max[j] && !(fabsf(row_mid - r0.y) > r2.w + 0.5f)) rows |= 1u << j;
                 }
             }
             __syncwarp();                                    // previous bucket's readers are done
             sp[lane][0] = r0; sp[lane][1] = r1; sp[lane][2] = r2;
             s_gid[warp][lane] = gid;
-            s_rows[warp][lane] = rows & alive_rows;
+            s_rows[warp][lane] = rows;
             __syncwarp();
         }
 
@@ -379,38 +386,42 @@ render_backward_kernel(ViewParams vp, int T_tiles, const ImageHeader* __restrict
             const float dx = fsub(a.x, pfx);
             const float cxdx = fmul(dx, a.z);                // shared by the lane's pixels: same column
             float v_mx = 0.f, v_my = 0.f, v_cx = 0.f, v_cy = 0.f, v_cw = 0.f, v_c0 = 0.f, v_c1 = 0.f, v_c2 = 0.f, v_o = 0.f;
+            // Row pairs are taken in groups of GRP: one warp-uniform branch per group, and inside a group the pixels are
+            // evaluated WITHOUT branches (a pixel that does not take the splat gets alpha = G = 0, which makes every term
+            // below an exact zero and leaves T untouched), so the GRP dependency chains interleave in the issue stream.
 #pragma unroll
-            for (int j = 0; j < BWD_ROWPAIRS; ++j) {
-                if (!((rows >> j) & 1u)) continue;           // warp-uniform
-                if (k < rel[j]) {
+            for (int jg = 0; jg < BWD_ROWPAIRS; jg += GRP) {
+                if (!((rows >> jg) & ((1u << GRP) - 1u))) continue;              // warp-uniform
+#pragma unroll
+                for (int u = 0; u < GRP; ++u) {
+                    const int j = jg + u;
                     const float dy = fsub(a.y, (float)(qy0 + 2 * j));
                     // splat_power(dx, dy, cx, cy, cz) with the dx*cx product hoisted (same operation order)
                     const float power = fsub(fmul(ffma(dx, cxdx, fmul(dy, fmul(dy, b.x))), -0.5f), fmul(dy, fmul(dx, a.w)));
-                    if (power <= 0.0f) {
-                        const float G = expf(power);
-                        const float alpha = fminf(0.99f, fmul(b.y, G));
-                        if (alpha >= (1.0f / 255.0f)) {
-                            const float one_m = fsub(1.0f, alpha);
-                            const float T = Tr[j];
-                            const float dchannel_dcolor = alpha * T;
-                            float alpha_inverse;                                  // 1/(1-alpha), 1-alpha in [0.01, 1]: MUFU.RCP
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(alpha_inverse) : "f"(one_m));
-                            float dL_dalpha;
-                            a0[j] += dchannel_dcolor * b.z; v_c0 += dchannel_dcolor * g0[j]; dL_dalpha = ((b.z * T) + alpha_inverse * a0[j]) * g0[j];
-                            a1[j] += dchannel_dcolor * b.w; v_c1 += dchannel_dcolor * g1[j]; dL_dalpha += ((b.w * T) + alpha_inverse * a1[j]) * g1[j];
-                            a2[j] += dchannel_dcolor * c2; v_c2 += dchannel_dcolor * g2[j]; dL_dalpha += ((c2 * T) + alpha_inverse * a2[j]) * g2[j];
-                            Tr[j] = fmul(T, one_m);
-                            // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per splat below
-                            const float gdl = G * dL_dalpha;                      // = dL_dG / opacity
-                            const float gdx = gdl * dx, gdy = gdl * dy;
-                            v_mx += gdx * a.z + gdy * a.w;                        // -> * (-opacity * 0.5 * W)
-                            v_my += gdy * b.x + gdx * a.w;                        // -> * (-opacity * 0.5 * H)
-                            v_cx += gdx * dx;                                     // -> * (-0.5 * opacity)
-                            v_cy += gdx * dy;
-                            v_cw += gdy * dy;
-                            v_o += gdl;
-                        }
-                    }
+                    const float Gx = expf(fminf(power, 0.0f));
+                    const float ax = fminf(0.99f, fmul(b.y, Gx));
+                    const bool take = (((rows >> j) & 1u) != 0) & (k < rel[j]) & (power <= 0.0f) & (ax >= (1.0f / 255.0f));
+                    const float G = take ? Gx : 0.0f;
+                    const float alpha = take ? ax : 0.0f;
+                    const float one_m = fsub(1.0f, alpha);
+                    const float T = Tr[j];
+                    const float dchannel_dcolor = alpha * T;
+                    float alpha_inverse;                                  // 1/(1-alpha), 1-alpha in [0.01, 1]: MUFU.RCP
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(alpha_inverse) : "f"(one_m));
+                    float dL_dalpha;
+                    a0[j] += dchannel_dcolor * b.z; v_c0 += dchannel_dcolor * g0[j]; dL_dalpha = ((b.z * T) + alpha_inverse * a0[j]) * g0[j];
+                    a1[j] += dchannel_dcolor * b.w; v_c1 += dchannel_dcolor * g1[j]; dL_dalpha += ((b.w * T) + alpha_inverse * a1[j]) * g1[j];
+                    a2[j] += dchannel_dcolor * c2; v_c2 += dchannel_dcolor * g2[j]; dL_dalpha += ((c2 * T) + alpha_inverse * a2[j]) * g2[j];
+                    Tr[j] = fmul(T, one_m);
+                    // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per splat below
+                    const float gdl = G * dL_dalpha;                      // = dL_dG / opacity
+                    const float gdx = gdl * dx, gdy = gdl * dy;
+                    v_mx += gdx * a.z + gdy * a.w;                        // -> * (-opacity * 0.5 * W)
+                    v_my += gdy * b.x + gdx * a.w;                        // -> * (-opacity * 0.5 * H)
+                    v_cx += gdx * dx;                                     // -> * (-0.5 * opacity)
+                    v_cy += gdx * dy;
+                    v_cw += gdy * dy;
+                    v_o += gdl;
                 }
             }
             // v_o != 0 iff some pixel of this lane contributed?  gdl can be exactly 0 (zero image gradient): then every
@@ -474,16 +485,26 @@ int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, con
     const int T = vp.grid_x * vp.grid_y;
     live_scan_kernel<<<1, 1024, 0, s>>>(T, img.max_contrib, img.live_offsets, img.hdr);
     GLIC_LAUNCH_CHECK();
+    // RP = row pairs per lane (8: one warp per bucket, 4: two warps share a bucket's tile); GRP = row pairs evaluated
+    // branch-free together.  Tuning knobs for the profiles/ sweep; the default is the measured best.
+    static const int rp = getenv("GLIC_BWD_RP") ? atoi(getenv("GLIC_BWD_RP")) : 8;
+    static const int grp = getenv("GLIC_BWD_GRP") ? atoi(getenv("GLIC_BWD_GRP")) : 2;
+    using Kern = void (*)(ViewParams, int, ImageHeader*, const uint2*, const uint32_t*, const float4*, const uint32_t*,
+                          const uint32_t*, const float4*, const uint32_t*, const float*, const float*, float*, float*, float*, float*);
+    static Kern kern = nullptr;
     static int blocks = 0;
-    if (blocks == 0) {
+    if (!kern) {
+        kern = rp == 8 ? (grp >= 4 ? render_backward_kernel<8, 4, 3> : grp == 2 ? render_backward_kernel<8, 2, 4> : render_backward_kernel<8, 1, 4>)
+                       : (grp >= 4 ? render_backward_kernel<4, 4, 5> : grp == 2 ? render_backward_kernel<4, 2, 6> : render_backward_kernel<4, 1, 6>);
         int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_backward_kernel, BWD_WARPS * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BWD_WARPS * 32, 0);
         blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const int64_t need = (max_buckets + BWD_WARPS - 1) / BWD_WARPS;
-    render_backward_kernel<<<(unsigned)std::min<int64_t>(blocks, need), BWD_WARPS * 32, 0, s>>>(
+    const int parts = rp == 8 ? 1 : 2;
+    const int64_t need = (max_buckets * parts + BWD_WARPS - 1) / BWD_WARPS;
+    kern<<<(unsigned)std::min<int64_t>(blocks, need), BWD_WARPS * 32, 0, s>>>(
         vp, T, img.hdr, img.ranges, point_list, g.rec, img.bucket_offsets, img.live_offsets, smp.ckpt, img.n_contrib,
         img.pixel_colors, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors);
     GLIC_LAUNCH_CHECK();
