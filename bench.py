@@ -105,12 +105,30 @@ def algorithmic_bytes(P, V, R, HW, M):
     return A1, per_stage
 
 
+def physical_cores():
+    """Physical cores available to this process (SMT siblings slow the OpenMP oracle down, measured)."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        cores, cur = set(), {}
+        for line in open("/proc/cpuinfo"):
+            if ":" not in line:
+                if "processor" in cur and int(cur["processor"]) in allowed:
+                    cores.add((cur.get("physical id", "0"), cur.get("core id", cur["processor"])))
+                cur = {}
+                continue
+            k, v = line.split(":", 1)
+            cur[k.strip()] = v.strip()
+        return max(1, len(cores))
+    except Exception:
+        return max(1, (os.cpu_count() or 2) // 2)
+
+
 def cpu_baseline(cfg, sample_P, threads_note=True):
     """CPU oracle (port) timed on the host cores on a bounded sample: same recipe, fewer Gaussians."""
     from gaussian_lic_b200 import synthetic as syn
     from oracle.oracle import Oracle
     o = Oracle(np.float32)
-    o.set_threads(len(os.sched_getaffinity(0)))            # torchrun exports OMP_NUM_THREADS=1; use the host cores we have
+    o.set_threads(physical_cores())                        # torchrun exports OMP_NUM_THREADS=1; use the host cores we have
     g, cam = syn.make_scene(cfg, P=sample_P)
     gt = syn.make_gt_image(cam["W"], cam["H"])
     t0 = time.perf_counter()
