@@ -116,7 +116,7 @@ struct __align__(16) PassSmem {
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(KeyT) == 4 ? 5 : 3)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, const unsigned int* __restrict__ n_dev,
                      int shift, int bits, const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status,
@@ -154,7 +154,8 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         uint32_t r = 0;
         uint32_t bpeers = vmask;
-        if (sizeof(KeyT) == 4) {   // 32-bit keys: peers from `bits` ballots (cost independent of the digit distribution)
+        {   // peers from `bits` ballots: cost independent of the digit distribution (MATCH.ANY stalls ~2x longer on
+            // passes whose 256 digits are all populated; ncu: profiles/r01_prof_sort_raw.csv)
 #pragma unroll
             for (int b = 0; b < RADIX_BITS; ++b) {
                 if (b < bits) {
@@ -165,7 +166,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
             }
         }
         if (valid) {
-            const uint32_t peers = sizeof(KeyT) == 4 ? bpeers : __match_any_sync(vmask, d);
+            const uint32_t peers = bpeers;
             const int leader = __ffs(peers) - 1;
             uint32_t c = 0;
             if (lane == leader) {

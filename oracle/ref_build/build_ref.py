@@ -28,6 +28,7 @@ def sources():
     s = os.path.join(REF, "src")
     return [
         os.path.join(HERE, "ref_binding.cpp"),
+        os.path.join(HERE, "cub_sort.cu"),
         os.path.join(s, "rasterizer", "rasterizer.cpp"),
         os.path.join(s, "rasterizer", "rasterize_points.cu"),
         os.path.join(s, "rasterizer", "cuda_rasterizer", "forward.cu"),

@@ -118,6 +118,21 @@ void sparse_adam_step(std::vector<Tensor> params, std::vector<double> lrs, Tenso
     opt->step();
 }
 
+extern "C" int ref_cub_sort_pairs(void* temp, size_t* temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                                  const uint32_t* vals_in, uint32_t* vals_out, int64_t n, int end_bit, void* stream);
+
+// cub::DeviceRadixSort::SortPairs exactly as rasterizer_impl.cu:419-424 calls it; keys int64-viewed u64, values int32-viewed u32.
+// `temp` may be an empty tensor: then only the required size is returned.
+int64_t cub_sort_pairs(Tensor temp, Tensor keys_in, Tensor keys_out, Tensor vals_in, Tensor vals_out, int64_t end_bit) {
+    size_t bytes = (size_t)temp.numel();
+    const int err = ref_cub_sort_pairs(temp.numel() ? temp.data_ptr() : nullptr, &bytes,
+                                       reinterpret_cast<const uint64_t*>(keys_in.data_ptr()), reinterpret_cast<uint64_t*>(keys_out.data_ptr()),
+                                       reinterpret_cast<const uint32_t*>(vals_in.data_ptr()), reinterpret_cast<uint32_t*>(vals_out.data_ptr()),
+                                       keys_in.numel(), (int)end_bit, nullptr);
+    TORCH_CHECK(err == 0, "cub::DeviceRadixSort::SortPairs failed: ", err);
+    return (int64_t)bytes;
+}
+
 Tensor fused_ssim_autograd(Tensor img1, Tensor img2) { return loss_utils::fused_ssim(img1, img2); }
 Tensor l1_autograd(Tensor a, Tensor b) { return loss_utils::l1_loss(a, b); }
 
@@ -134,6 +149,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("fused_ssim_autograd", &fused_ssim_autograd);
     m.def("l1_autograd", &l1_autograd);
     m.def("sparse_adam_step", &sparse_adam_step);
+    m.def("cub_sort_pairs", &cub_sort_pairs);
     m.def("slice_geom", &slice_geom);
     m.def("slice_binning", &slice_binning);
     m.def("slice_image", &slice_image);
