@@ -134,13 +134,18 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     // depth sort while the host waits for exactly that copy (the reference blocks here too, rasterizer_impl.cu:398, but
     // with an idle GPU).
     static thread_local unsigned int* r_pinned = nullptr;
-    static thread_local cudaEvent_t r_event = nullptr;
+    static thread_local cudaEvent_t r_ready = nullptr, r_event = nullptr;
+    static thread_local cudaStream_t r_stream = nullptr;      // the 4-byte copy must not sit in front of the depth sort
     if (!r_pinned) {
         GLIC_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&r_pinned), sizeof(unsigned int), cudaHostAllocDefault));
+        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&r_ready, cudaEventDisableTiming));
         GLIC_CUDA_TRY(cudaEventCreateWithFlags(&r_event, cudaEventDisableTiming));
+        GLIC_CUDA_TRY(cudaStreamCreateWithFlags(&r_stream, cudaStreamNonBlocking));
     }
-    GLIC_CUDA_TRY(cudaMemcpyAsync(r_pinned, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-    GLIC_CUDA_TRY(cudaEventRecord(r_event, s));
+    GLIC_CUDA_TRY(cudaEventRecord(r_ready, s));
+    GLIC_CUDA_TRY(cudaStreamWaitEvent(r_stream, r_ready, 0));
+    GLIC_CUDA_TRY(cudaMemcpyAsync(r_pinned, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, r_stream));
+    GLIC_CUDA_TRY(cudaEventRecord(r_event, r_stream));
     {   // depth-first binning: order the Gaussians by (depth, index) once, then prefix-sum their tile counts in that order
         StageTimer _t(GLIC_STAGE_SORT, s);
         const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
