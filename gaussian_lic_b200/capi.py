@@ -58,6 +58,11 @@ def _load():
         "glic_fused_ssim_backward": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_l1_ssim_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
         "glic_knn_mean_dist2": (i32, [i32, vp, vp, vp, sz, vp]),
+        "glic_packed_floats": (sz, [u32, u32]),
+        "glic_packed_offsets": (i32, [u32, u32, C.POINTER(sz)]),
+        "glic_activations_forward": (i32, [i32, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_activations_backward": (i32, [i32, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_adam_update_packed": (i32, [vp, vp, vp, vp, vp, C.POINTER(f32), f32, f32, f32, u32, u32, vp]),
         "glic_p2p_buffer_bytes": (sz, [sz, sz]),
         "glic_p2p_alloc": (i32, [sz, C.POINTER(vp), C.c_char_p]),
         "glic_p2p_open": (i32, [C.c_char_p, C.POINTER(vp)]),

@@ -164,6 +164,28 @@ GLIC_API int glic_adam_update(float* param, const float* grad, float* exp_avg, f
                      uint32_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Packed model step (extension, no single reference symbol).  The model lives in one planar buffer
+ *     rotation[4P] | xyz[3P] | log-scale[3P] | opacity logit[P] | dc[3P] | sh-rest[3MP]      (glic_packed_offsets)
+ * which is also the layout of the packed gradient buffer (glic_p2p_allreduce_mean's payload).
+ *  - glic_activations_forward replaces GaussianModel::getOpacity / getScaling / getRotation (gaussian.cpp:147-175:
+ *    torch::sigmoid, torch::exp, normalize) with one kernel;
+ *  - glic_activations_backward applies their chain rule IN PLACE to the gradients glic_backward wrote (what autograd's
+ *    SigmoidBackward / ExpBackward / normalize backward do for the reference);
+ *  - glic_adam_update_packed is SparseGaussianAdam::custom_step (optim_utils.h:102-137) for all six groups in ONE
+ *    launch, element-wise identical to six glic_adam_update calls; lr6_host in buffer order
+ *    {rotation, xyz, scaling, opacity, f_dc, f_rest}.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_packed_floats(uint32_t P, uint32_t M);
+GLIC_API int glic_packed_offsets(uint32_t P, uint32_t M, size_t* offsets6_host);
+GLIC_API int glic_activations_forward(int P, const float* opacity_logit, const float* log_scale, const float* rot_raw,
+                                      float* opacity, float* scale, float* rot, void* stream);
+GLIC_API int glic_activations_backward(int P, const float* opacity, const float* scale, const float* rot_raw,
+                                       float* dL_dopacity, float* dL_dscale, float* dL_drot, void* stream);
+GLIC_API int glic_adam_update_packed(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                     const uint8_t* visible, const float* lr6_host, float b1, float b2, float eps,
+                                     uint32_t P, uint32_t M, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused SSIM.  Replaces fusedssimCUDA / fusedssim_backwardCUDA (fused-ssim/ssim.cu:186-365).
  * img*: [B,CH,H,W] contiguous.  Partial-derivative maps may be NULL in forward (train = false).
  * ------------------------------------------------------------------------------------- */
