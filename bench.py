@@ -197,7 +197,14 @@ def run_ours(args):
         from gaussian_lic_b200 import dist as gdist
         # the exchange step: our own two-shot all-reduce over NVLink peer memory (csrc/p2p.cu); --exchange nccl keeps
         # the library collective as the comparison
-        allreduce = (gdist.P2PGradAllReduce if args.exchange == "p2p" else gdist.GradAllReduce)(P, M, dev)
+        if args.exchange == "p2p":
+            try:
+                allreduce = gdist.P2PGradAllReduce(P, M, dev)
+            except RuntimeError as e:                          # raised on every rank together (dist.py): IPC not permitted here
+                print("[bench] %s -- falling back to the NCCL all-reduce" % (e,), file=sys.stderr)
+                args.exchange = "nccl"
+        if allreduce is None:
+            allreduce = gdist.GradAllReduce(P, M, dev)
         grads = allreduce.grads                           # backward writes straight into the collective's buffer
 
     def step():

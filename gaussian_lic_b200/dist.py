@@ -95,22 +95,42 @@ class P2PGradAllReduce:
         self.n_floats = int(P) * PackedGrads.floats_per_gaussian(M)
         self.n_vis = int(P)
         nbytes = int(self.lib.glic_p2p_buffer_bytes(self.n_floats, self.n_vis))
+        # Every phase that can fail locally (allocation, IPC export, IPC import) is followed by an exchange of the outcome,
+        # so that all ranks raise together instead of one rank leaving the others inside a collective.
         own, handle = C.c_void_p(), C.create_string_buffer(64)
-        capi.check(self.lib.glic_p2p_alloc(nbytes, C.byref(own), handle), "glic_p2p_alloc")
+        err = None
+        try:
+            capi.check(self.lib.glic_p2p_alloc(nbytes, C.byref(own), handle), "glic_p2p_alloc")
+        except Exception as e:                      # noqa: BLE001 - reported to every rank below
+            err = repr(e)
         self._own = own.value
-        handles = [None] * self.world
+        mine = (err, handle.raw)
+        infos = [mine] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, handle.raw, group=group)
-        else:
-            handles[0] = handle.raw
+            dist.all_gather_object(infos, mine, group=group)
         self._peers = (C.c_void_p * self.world)()
-        for q in range(self.world):
-            if q == self.rank:
-                self._peers[q] = self._own
-            else:
+        self._opened = []
+        bad = [(q, i[0]) for q, i in enumerate(infos) if i[0] is not None]
+        if not bad:
+            for q in range(self.world):
+                if q == self.rank:
+                    self._peers[q] = self._own
+                    continue
                 peer = C.c_void_p()
-                capi.check(self.lib.glic_p2p_open(handles[q], C.byref(peer)), "glic_p2p_open")
-                self._peers[q] = peer.value
+                try:
+                    capi.check(self.lib.glic_p2p_open(infos[q][1], C.byref(peer)), "glic_p2p_open")
+                    self._peers[q] = peer.value
+                    self._opened.append(peer.value)
+                except Exception as e:              # noqa: BLE001
+                    err = "rank %d -> %d: %r" % (self.rank, q, e)
+                    break
+            outcomes = [err] * self.world
+            if self.world > 1:
+                dist.all_gather_object(outcomes, err, group=group)
+            bad = [(q, o) for q, o in enumerate(outcomes) if o is not None]
+        if bad:
+            self._release()
+            raise RuntimeError("P2P gradient exchange unavailable: %s" % (bad,))
         raw = torch.as_tensor(_DevMem(self._own, nbytes), device=device)
         self._raw = raw
         f_bytes = (self.n_floats * 4 + 255) // 256 * 256
@@ -138,10 +158,14 @@ class P2PGradAllReduce:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)
-        for q in range(self.world):
-            if q != self.rank:
-                self.lib.glic_p2p_close(self._C.c_void_p(self._peers[q]))
-        self.lib.glic_p2p_free(self._C.c_void_p(self._own))
+        self._release()
+
+    def _release(self):
+        for p_ in getattr(self, "_opened", []):
+            self.lib.glic_p2p_close(self._C.c_void_p(p_))
+        self._opened = []
+        if getattr(self, "_own", None):
+            self.lib.glic_p2p_free(self._C.c_void_p(self._own))
         self._own = None
 
 

@@ -93,6 +93,39 @@ def test_argument_validation_without_gpu():
     assert lib.glic_knn_mean_dist2(-1, None, None, None, 0, None) == -1
 
 
+def test_packed_layout_and_exchange_sizes():
+    """Host-only entry points of the packed model step and of the exchange buffer."""
+    from gaussian_lic_b200 import capi
+    lib = capi.lib
+    off = (C.c_size_t * 6)()
+    for P, M in ((0, 15), (1, 0), (1000, 15), (500_000, 15)):
+        assert lib.glic_packed_offsets(P, M, off) == 0
+        k = (4, 3, 3, 1, 3, 3 * M)
+        want, acc = [], 0
+        for kk in k:
+            want.append(acc)
+            acc += P * kk
+        assert [int(o) for o in off] == want and lib.glic_packed_floats(P, M) == acc
+        assert int(off[0]) % 4 == 0                                        # rotations first: float4 stores stay aligned
+    assert lib.glic_packed_offsets(10, 15, None) == -1
+    # exchange buffer: floats, visibility bytes and the flag block, each padded to 256 B
+    n = lib.glic_packed_floats(500_000, 15)
+    b = lib.glic_p2p_buffer_bytes(n, 500_000)
+    assert b == -(-n * 4 // 256) * 256 + -(-500_000 // 256) * 256 + 256
+    assert lib.glic_p2p_buffer_bytes(0, 0) == 256
+    # argument validation, nothing launched
+    lr = (C.c_float * 6)(*([1e-3] * 6))
+    assert lib.glic_adam_update_packed(None, None, None, None, None, lr, 0.9, 0.999, 1e-15, 10, 15, None) == -1
+    assert lib.glic_adam_update_packed(None, None, None, None, None, lr, 0.9, 0.999, 1e-15, 0, 15, None) == 0
+    assert lib.glic_activations_forward(10, None, None, None, None, None, None, None) == -1
+    assert lib.glic_activations_forward(0, None, None, None, None, None, None, None) == 0
+    assert lib.glic_activations_backward(-1, None, None, None, None, None, None, None) == -1
+    peers = (C.c_void_p * 2)()
+    assert lib.glic_p2p_allreduce_mean(2, 2, peers, 10, 10, None) == -1     # rank out of range
+    assert lib.glic_p2p_allreduce_mean(0, 9, peers, 10, 10, None) == -1     # more ranks than one NVSwitch domain
+    assert lib.glic_p2p_alloc(1024, None, None) == -1
+
+
 def test_package_fails_loudly_without_library(tmp_path, monkeypatch):
     """No silent CPU/PyTorch fallback: a missing .so is an ImportError."""
     import importlib

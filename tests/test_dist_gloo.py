@@ -61,3 +61,30 @@ def test_packed_layout_and_view_sharding():
     views = [gdist.shard_views(8, r, 4) for r in range(4)]
     assert sorted(sum(views, [])) == list(range(8)) and all(len(v) == 2 for v in views)
     assert np.all([gdist.shard_views(8, 0, 1) == list(range(8))])
+
+
+def _p2p_fail_worker(rank, world, port, out_dir):
+    """Without a GPU the IPC allocation fails locally; every rank must learn it and raise together (no rank may be left
+    inside a collective)."""
+    import torch.distributed as dist
+    from gaussian_lic_b200 import dist as gdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    msg = "no error"
+    try:
+        gdist.P2PGradAllReduce(64, 15, torch.device("cpu"))
+    except RuntimeError as e:
+        msg = str(e)
+    dist.barrier()                                          # both ranks got out of the constructor
+    open(os.path.join(out_dir, "p2p%d.txt" % rank), "w").write(msg)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="exercises the no-GPU failure path")
+def test_p2p_setup_failure_is_collective(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_p2p_fail_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r_ in range(2):
+        msg = open(os.path.join(tmp_path, "p2p%d.txt" % r_)).read()
+        assert "P2P gradient exchange unavailable" in msg and "glic_p2p_alloc" in msg, msg
