@@ -170,6 +170,34 @@ class Oracle:
                                   self.real(b2), self.real(eps), C.c_uint32(N), C.c_uint32(Mm))
         return p, m, v
 
+    def adam_packed(self, params, grads, m, v, visible, lr6, M, b1=0.9, b2=0.999, eps=1e-15):
+        """SparseGaussianAdam over the planar model (buffer order rotation, xyz, scaling, opacity, f_dc, f_rest):
+        six per-group applications of A.10 -- the oracle of glic_adam_update_packed."""
+        p, mm, vv = (self._a(x).copy().reshape(-1) for x in (params, m, v))
+        g = self._a(grads).reshape(-1)
+        P = np.asarray(visible).shape[0]
+        off = 0
+        for k, lr in zip((4, 3, 3, 1, 3, 3 * M), lr6):
+            n = P * k
+            if n:
+                p[off:off + n], mm[off:off + n], vv[off:off + n] = (
+                    x.reshape(-1) for x in self.adam(p[off:off + n], g[off:off + n], mm[off:off + n], vv[off:off + n], visible, lr, b1, b2, eps))
+            off += n
+        return p, mm, vv
+
+    def activations(self, logits, log_scales, rots_raw):
+        a, b, c = self._a(logits).reshape(-1), self._a(log_scales), self._a(rots_raw)
+        P = a.shape[0]
+        op, sc, rot = np.zeros(P, self.dtype), np.zeros((P, 3), self.dtype), np.zeros((P, 4), self.dtype)
+        self.lib.glic_oracle_activations(C.c_int(P), _ptr(a), _ptr(b), _ptr(c), _ptr(op), _ptr(sc), _ptr(rot))
+        return op, sc, rot
+
+    def activations_backward(self, opacity, scales, rots_raw, dL_dopacity, dL_dscales, dL_drots):
+        op, sc, rr = self._a(opacity).reshape(-1), self._a(scales), self._a(rots_raw)
+        g1, g2, g3 = self._a(dL_dopacity).copy().reshape(-1), self._a(dL_dscales).copy(), self._a(dL_drots).copy()
+        self.lib.glic_oracle_activations_backward(C.c_int(op.shape[0]), _ptr(op), _ptr(sc), _ptr(rr), _ptr(g1), _ptr(g2), _ptr(g3))
+        return g1, g2, g3
+
     def knn(self, pts):
         p = self._a(pts)
         out = np.zeros(p.shape[0], self.dtype)

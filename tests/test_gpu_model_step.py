@@ -115,3 +115,42 @@ def test_native_iteration_descends_and_graph_replays():
     assert not rast.finish()
     assert all(np.isfinite(losses)) and bool(torch.isfinite(mdl.params).all())
     assert losses[-1] < losses[0], losses
+
+
+def test_model_step_matches_cpu_oracle(oracle32):
+    """CUDA activations / chain rule / packed Adam against the CPU restatement (oracle/glic_oracle.c)."""
+    from gaussian_lic_b200 import capi
+    lib, P, M = capi.lib, 3001, 15
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 2, P).astype(np.float32)
+    b = rng.normal(-4, 0.6, (P, 3)).astype(np.float32)
+    c = rng.normal(0, 1, (P, 4)).astype(np.float32)
+    w1, w2, w3 = (rng.normal(size=s).astype(np.float32) for s in ((P,), (P, 3), (P, 4)))
+    o_op, o_sc, o_rot = oracle32.activations(a, b, c)
+    o_g = oracle32.activations_backward(o_op, o_sc, c, w1, w2, w3)
+    t = lambda x: torch.as_tensor(x).cuda()
+    da, db, dc_ = t(a), t(b), t(c)
+    op, sc, rot = torch.empty(P, device="cuda"), torch.empty(P, 3, device="cuda"), torch.empty(P, 4, device="cuda")
+    capi.check(lib.glic_activations_forward(P, capi.ptr(da), capi.ptr(db), capi.ptr(dc_), capi.ptr(op), capi.ptr(sc),
+                                            capi.ptr(rot), None), "act")
+    g1, g2, g3 = t(w1), t(w2), t(w3)
+    capi.check(lib.glic_activations_backward(P, capi.ptr(op), capi.ptr(sc), capi.ptr(dc_), capi.ptr(g1), capi.ptr(g2),
+                                             capi.ptr(g3), None), "act_bwd")
+    for mine, ref, what in ((op, o_op, "opacity"), (sc, o_sc, "scale"), (rot, o_rot, "rotation"), (g1, o_g[0], "d opacity"),
+                            (g2, o_g[1], "d scale"), (g3, o_g[2], "d rotation")):
+        err = np.abs(mine.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err <= 5e-6, (what, err)             # expf / division rounding only
+    n = P * 59
+    p, g, m, v = (rng.normal(size=n).astype(np.float32) for _ in range(4))
+    g *= 1e-3; m *= 1e-3; v = (v * 1e-3) ** 2
+    vis = (rng.uniform(size=P) < 0.7).astype(np.uint8)
+    lr6 = [1e-3, 1.6e-4, 5e-3, 5e-2, 2.5e-3, 1.25e-4]
+    op_, om_, ov_ = oracle32.adam_packed(p, g, m, v, vis, lr6, M)
+    dp, dg, dm, dv, dvis = t(p), t(g), t(m), t(v), t(vis)
+    capi.check(lib.glic_adam_update_packed(capi.ptr(dp), capi.ptr(dg), capi.ptr(dm), capi.ptr(dv), capi.ptr(dvis),
+                                           (C.c_float * 6)(*lr6), 0.9, 0.999, 1e-15, P, M, None), "packed")
+    torch.cuda.synchronize()
+    # same tolerance as the per-group Adam test: nvcc contracts b1*m + (1-b1)*g into an fma
+    np.testing.assert_allclose(dm.cpu().numpy(), om_, rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dv.cpu().numpy(), ov_, rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(dp.cpu().numpy(), op_, rtol=1e-5, atol=2e-6)

@@ -61,3 +61,61 @@ def test_loss_gradient_finite_differences(oracle64):
         a = img.copy(); a[idx] -= h; Lm, _ = o.loss(a, gt, grad=False)
         fd = (Lp - Lm) / (2 * h)
         assert abs(fd - g[idx]) <= 1e-6 * max(1.0, abs(fd) * 1e3), (fd, g[idx])
+
+
+def test_activation_chain_rule_matches_finite_differences():
+    """Oracle of the packed model step: the in-place chain rule of sigmoid / exp / normalize
+    (gaussian.cpp:147-175 + autograd) against central differences of the f64 forward."""
+    from oracle.oracle import Oracle
+    o = Oracle(np.float64)
+    rng = np.random.default_rng(12)
+    P = 40
+    a, b, c = rng.normal(0, 2, P), rng.normal(-4, 0.6, (P, 3)), rng.normal(0, 1, (P, 4))
+    w1, w2, w3 = rng.normal(size=P), rng.normal(size=(P, 3)), rng.normal(size=(P, 4))
+    op, sc, rot = o.activations(a, b, c)
+    np.testing.assert_allclose(op, 1.0 / (1.0 + np.exp(-a)), rtol=1e-14)
+    np.testing.assert_allclose(sc, np.exp(b), rtol=1e-14)
+    np.testing.assert_allclose(np.linalg.norm(rot, axis=1), 1.0, rtol=1e-14)
+    g1, g2, g3 = o.activations_backward(op, sc, c, w1, w2, w3)
+
+    def loss(a_, b_, c_):
+        x, y, z = o.activations(a_, b_, c_)
+        return (w1 * x).sum() + (w2 * y).sum() + (w3 * z).sum()
+
+    h = 1e-6
+    for arr, grad, idxs in ((a, g1, [(i,) for i in range(0, P, 7)]), (b, g2, [(i, i % 3) for i in range(0, P, 7)]),
+                            (c, g3, [(i, i % 4) for i in range(0, P, 5)])):
+        for idx in idxs:
+            plus, minus = arr.copy(), arr.copy()
+            plus[idx] += h
+            minus[idx] -= h
+            args_p = [plus if x is arr else x for x in (a, b, c)]
+            args_m = [minus if x is arr else x for x in (a, b, c)]
+            fd = (loss(*args_p) - loss(*args_m)) / (2 * h)
+            assert abs(fd - grad[idx]) <= 1e-7 * max(1.0, abs(fd)), (idx, fd, grad[idx])
+    # the unit quaternion's gradient is tangent: no component along q
+    assert np.abs((g3 * rot).sum(1)).max() < 1e-12
+
+
+def test_packed_adam_oracle_equals_per_group_adam():
+    from oracle.oracle import Oracle
+    o = Oracle(np.float32)
+    rng = np.random.default_rng(3)
+    P, M = 37, 15
+    n = P * 59
+    p, g, m, v = (rng.normal(size=n).astype(np.float32) for _ in range(4))
+    v = v * v
+    vis = (rng.uniform(size=P) < 0.6).astype(np.uint8)
+    lr6 = [1e-3, 1.6e-4, 5e-3, 5e-2, 2.5e-3, 1.25e-4]
+    p2, m2, v2 = o.adam_packed(p, g, m, v, vis, lr6, M)
+    # rotation block by hand: element j of the block belongs to Gaussian j // 4
+    on = np.repeat(vis.astype(bool), 4)
+    mm = np.float32(0.9) * m[:4 * P] + (np.float32(1) - np.float32(0.9)) * g[:4 * P]
+    vv = np.float32(0.999) * v[:4 * P] + (np.float32(1) - np.float32(0.999)) * g[:4 * P] * g[:4 * P]
+    want = p[:4 * P] + np.where(on, -np.float32(lr6[0]) * mm / (np.sqrt(vv) + np.float32(1e-15)), 0).astype(np.float32)
+    np.testing.assert_allclose(p2[:4 * P], want, rtol=2e-6, atol=1e-7)
+    assert np.array_equal(p2[:4 * P][~on], p[:4 * P][~on]) and np.array_equal(m2[:4 * P][~on], m[:4 * P][~on])
+    # sh-rest block starts after 14 floats per Gaussian and has 45 per Gaussian
+    on_sh = np.repeat(vis.astype(bool), 45)
+    assert np.array_equal(p2[14 * P:][~on_sh], p[14 * P:][~on_sh])
+    assert not np.array_equal(p2[14 * P:][on_sh], p[14 * P:][on_sh])
