@@ -133,15 +133,21 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     // R is complete as soon as the preprocess kernel is: ship it to pinned host memory NOW and keep the GPU busy with the
     // depth sort while the host waits for exactly that copy (the reference blocks here too, rasterizer_impl.cu:398, but
     // with an idle GPU).
-    static thread_local unsigned int* r_pinned = nullptr;
-    static thread_local cudaEvent_t r_ready = nullptr, r_event = nullptr;
-    static thread_local cudaStream_t r_stream = nullptr;      // the 4-byte copy must not sit in front of the depth sort
-    if (!r_pinned) {
-        GLIC_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&r_pinned), sizeof(unsigned int), cudaHostAllocDefault));
-        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&r_ready, cudaEventDisableTiming));
-        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&r_event, cudaEventDisableTiming));
-        GLIC_CUDA_TRY(cudaStreamCreateWithFlags(&r_stream, cudaStreamNonBlocking));
+    struct RChannel { unsigned int* pinned; cudaEvent_t ready, done; cudaStream_t stream; };
+    static thread_local RChannel r_channels[64] = {};        // one per device: streams and events are device-bound
+    int dev = 0;
+    GLIC_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("forward_preprocess: device index out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
+    RChannel& rc = r_channels[dev];
+    if (!rc.pinned) {
+        GLIC_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&rc.pinned), sizeof(unsigned int), cudaHostAllocDefault));
+        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&rc.ready, cudaEventDisableTiming));
+        GLIC_CUDA_TRY(cudaEventCreateWithFlags(&rc.done, cudaEventDisableTiming));
+        GLIC_CUDA_TRY(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));   // the 4-byte copy must not sit in front of the depth sort
     }
+    unsigned int* r_pinned = rc.pinned;
+    cudaEvent_t r_ready = rc.ready, r_event = rc.done;
+    cudaStream_t r_stream = rc.stream;
     GLIC_CUDA_TRY(cudaEventRecord(r_ready, s));
     GLIC_CUDA_TRY(cudaStreamWaitEvent(r_stream, r_ready, 0));
     GLIC_CUDA_TRY(cudaMemcpyAsync(r_pinned, &g.hdr->total, sizeof(unsigned int), cudaMemcpyDeviceToHost, r_stream));

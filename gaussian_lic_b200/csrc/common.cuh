@@ -117,6 +117,16 @@ struct GeomState {
     }
 };
 
+// Function attributes (opt-in dynamic shared memory) are per device: run `fn` once per (call site, device).
+// `flags` is the call site's own static array.
+inline bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 struct ImageHeader {
     long long num_rendered;     // R
     unsigned int num_buckets;   // B

@@ -344,71 +344,67 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
     // ---- phase 3: colour of the survivors -----------------------------------------------------------------
     if (sh_tma) mbar_wait(&s_bar, 0);      // (the walk's __syncthreads order thread 0's barrier init before every wait)
     if (cnt > 0) {
-        {
-            {
-                tiles = cnt;
-                radius = irad;
-                depth = tz;
-                float red = 0.f, green = 0.f;
-                if (!no_color) {
-                    // SH -> RGB (forward.cu:29-77); tolerance-pinned, natural arithmetic.
-                    float dx = px - s_cam[0], dy = py - s_cam[1], dz = pz - s_cam[2];
-                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    dx *= inv; dy *= inv; dz *= inv;
-                    float res[3];
+        tiles = cnt;
+        radius = irad;
+        depth = tz;
+        float red = 0.f, green = 0.f;
+        if (!no_color) {
+            // SH -> RGB (forward.cu:29-77); tolerance-pinned, natural arithmetic.
+            float dx = px - s_cam[0], dy = py - s_cam[1], dz = pz - s_cam[2];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv; dy *= inv; dz *= inv;
+            float res[3];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) res[ch] = kSH_C0 * dc[3 * idx + ch];
-                    if (D > 0) {
-                        const float* s = sh_tma ? (&s_sh[0][0] + (size_t)tid * K)
-                                                : (sh_staged ? (s_sh[warp] + lane * K) : (sh + (size_t)idx * K));
-                        const float x = dx, y = dy, z = dz;
-                        float b[15];
-                        b[0] = -kSH_C1 * y; b[1] = kSH_C1 * z; b[2] = -kSH_C1 * x;
-                        int nb = 3;
-                        if (D > 1) {
-                            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                            b[3] = kSH_C2[0] * xy; b[4] = kSH_C2[1] * yz; b[5] = kSH_C2[2] * (2.0f * zz - xx - yy);
-                            b[6] = kSH_C2[3] * xz; b[7] = kSH_C2[4] * (xx - yy);
-                            nb = 8;
-                            if (D > 2) {
-                                b[8] = kSH_C3[0] * y * (3.0f * xx - yy);
-                                b[9] = kSH_C3[1] * xy * z;
-                                b[10] = kSH_C3[2] * y * (4.0f * zz - xx - yy);
-                                b[11] = kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                                b[12] = kSH_C3[4] * x * (4.0f * zz - xx - yy);
-                                b[13] = kSH_C3[5] * z * (xx - yy);
-                                b[14] = kSH_C3[6] * x * (xx - 3.0f * yy);
-                                nb = 15;
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < 15; ++k) {
-                            if (k < nb) {
-                                res[0] += b[k] * s[3 * k + 0];
-                                res[1] += b[k] * s[3 * k + 1];
-                                res[2] += b[k] * s[3 * k + 2];
-                            }
-                        }
+            for (int ch = 0; ch < 3; ++ch) res[ch] = kSH_C0 * dc[3 * idx + ch];
+            if (D > 0) {
+                const float* s = sh_tma ? (&s_sh[0][0] + (size_t)tid * K)
+                                        : (sh_staged ? (s_sh[warp] + lane * K) : (sh + (size_t)idx * K));
+                const float x = dx, y = dy, z = dz;
+                float b[15];
+                b[0] = -kSH_C1 * y; b[1] = kSH_C1 * z; b[2] = -kSH_C1 * x;
+                int nb = 3;
+                if (D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    b[3] = kSH_C2[0] * xy; b[4] = kSH_C2[1] * yz; b[5] = kSH_C2[2] * (2.0f * zz - xx - yy);
+                    b[6] = kSH_C2[3] * xz; b[7] = kSH_C2[4] * (xx - yy);
+                    nb = 8;
+                    if (D > 2) {
+                        b[8] = kSH_C3[0] * y * (3.0f * xx - yy);
+                        b[9] = kSH_C3[1] * xy * z;
+                        b[10] = kSH_C3[2] * y * (4.0f * zz - xx - yy);
+                        b[11] = kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                        b[12] = kSH_C3[4] * x * (4.0f * zz - xx - yy);
+                        b[13] = kSH_C3[5] * z * (xx - yy);
+                        b[14] = kSH_C3[6] * x * (xx - 3.0f * yy);
+                        nb = 15;
                     }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        res[ch] += 0.5f;
-                        if (res[ch] < 0.0f) clampbits |= 1u << ch;
-                        res[ch] = fmaxf(res[ch], 0.0f);
-                    }
-                    red = res[0]; green = res[1]; blue = res[2];
                 }
-                r0 = make_float4(mx, my, cox, coy);
-                r1 = make_float4(coz, o, red, green);
-                // conservative vertical half-extent of {alpha >= 1/255} (dy^2 <= 2*thr*cox/det(conic)); falls back to the
-                // looser 3.33-sigma bound from the radius when det cancels badly.  Used by the render kernel's row cull.
-                {
-                    const float thr2 = __logf(255.0f * o) + 1e-3f;
-                    const float prod = cox * coz, dcon = prod - coy * coy;
-                    hy = 1.11f * (float)irad + 1.0f;
-                    if (dcon > 1e-3f * prod) hy = fminf(hy, sqrtf(2.0f * thr2 * cox / dcon) * 1.001f + 0.01f);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) {
+                    if (k < nb) {
+                        res[0] += b[k] * s[3 * k + 0];
+                        res[1] += b[k] * s[3 * k + 1];
+                        res[2] += b[k] * s[3 * k + 2];
+                    }
                 }
             }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                res[ch] += 0.5f;
+                if (res[ch] < 0.0f) clampbits |= 1u << ch;
+                res[ch] = fmaxf(res[ch], 0.0f);
+            }
+            red = res[0]; green = res[1]; blue = res[2];
+        }
+        r0 = make_float4(mx, my, cox, coy);
+        r1 = make_float4(coz, o, red, green);
+        // conservative vertical half-extent of {alpha >= 1/255} (dy^2 <= 2*thr*cox/det(conic)); falls back to the
+        // looser 3.33-sigma bound from the radius when det cancels badly.  Used by the render kernel's row cull.
+        {
+            const float thr2 = __logf(255.0f * o) + 1e-3f;
+            const float prod = cox * coz, dcon = prod - coy * coy;
+            hy = 1.11f * (float)irad + 1.0f;
+            if (dcon > 1e-3f * prod) hy = fminf(hy, sqrtf(2.0f * thr2 * cox / dcon) * 1.001f + 0.01f);
         }
     }
 
@@ -524,10 +520,9 @@ int launch_preprocess_forward(int P, int D, int M, const float* means, const flo
     GLIC_CUDA_TRY(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
     GLIC_CUDA_TRY(cudaMemsetAsync(g.scan_status, 0, sizeof(unsigned long long) * (blocks + 1), s));
     const size_t dyn = sizeof(float) * (PRE_THREADS / 32) * 32 * SH_ROW_MAX + sizeof(WalkSmem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) {
         GLIC_CUDA_TRY(cudaFuncSetAttribute(preprocess_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        attr_set = true;
     }
     preprocess_forward_kernel<<<blocks, PRE_THREADS, dyn, s>>>(P, D, M, means, scales, mod,
                                                              reinterpret_cast<const float4*>(rots), opac, dc, sh, vp,

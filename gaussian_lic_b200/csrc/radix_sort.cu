@@ -275,11 +275,10 @@ static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* 
     const size_t used = sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)passes * blocks * RADIX);
     GLIC_CUDA_TRY(cudaMemsetAsync(temp, 0, used, s));
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) {
         GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(PassSmem<KeyT>)));
-        attr_set = true;
     }
     int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
     sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, n_dev, passes, end_bit, t.hist);
