@@ -58,6 +58,11 @@ def _load():
         "glic_fused_ssim_backward": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_l1_ssim_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
         "glic_knn_mean_dist2": (i32, [i32, vp, vp, vp, sz, vp]),
+        "glic_ply_bytes": (sz, [u32, u32]),
+        "glic_ply_write": (i32, [C.c_char_p, u32, u32, vp, vp, vp, vp, vp, vp]),
+        "glic_ply_write_packed": (i32, [C.c_char_p, u32, u32, vp]),
+        "glic_ply_read_header": (i32, [C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(sz)]),
+        "glic_ply_read": (i32, [C.c_char_p, u32, u32, vp, vp, vp, vp, vp, vp]),
         "glic_packed_floats": (sz, [u32, u32]),
         "glic_packed_offsets": (i32, [u32, u32, C.POINTER(sz)]),
         "glic_activations_forward": (i32, [i32, vp, vp, vp, vp, vp, vp, vp]),

@@ -80,6 +80,30 @@ class PackedModel:
                                                     capi.ptr(self.exp_avg_sq), capi.ptr(visible), self.lr6, self.b1, self.b2,
                                                     self.eps, self.P, self.M, stream), "adam_update_packed")
 
+    # ---- on-disk map (GaussianModel::saveMap, gaussian.cpp:305-397) ---------------------------------------------------
+    def save_map(self, path):
+        """point_cloud.ply in the reference's layout, byte-identical to its writer for the same parameters."""
+        host = self.params.detach().to("cpu").contiguous()
+        capi.check(self.lib.glic_ply_write_packed(str(path).encode(), self.P, self.M, C.c_void_p(host.data_ptr())), "ply_write_packed")
+
+    @staticmethod
+    def load_map(path, device, degree=None, **kw):
+        """Raw parameters from a Gaussian-LIC / glic map file -> PackedModel (Adam state zeroed)."""
+        import numpy as np
+        lib = capi.lib
+        P, M = C.c_uint32(), C.c_uint32()
+        capi.check(lib.glic_ply_read_header(str(path).encode(), C.byref(P), C.byref(M), None), "ply_read_header")
+        P, M = P.value, M.value
+        a = dict(means=np.zeros((P, 3), np.float32), dc=np.zeros((P, 1, 3), np.float32), sh=np.zeros((P, M, 3), np.float32),
+                 opacity_logits=np.zeros(P, np.float32), log_scales=np.zeros((P, 3), np.float32), rots=np.zeros((P, 4), np.float32))
+        vp = lambda x: x.ctypes.data_as(C.c_void_p) if x.size else None
+        capi.check(lib.glic_ply_read(str(path).encode(), P, M, vp(a["means"]), vp(a["dc"]), vp(a["sh"]), vp(a["opacity_logits"]),
+                                     vp(a["log_scales"]), vp(a["rots"])), "ply_read")
+        deg = {0: 0, 3: 1, 8: 2, 15: 3}.get(M) if degree is None else degree
+        a["dc"] = a["dc"].reshape(P, 3)
+        a["degree"] = deg
+        return PackedModel(a, device, **kw)
+
     # ---- one mapping iteration (asynchronous; CUDA-graph capturable) -------------------------------------------
     def iteration(self, rast, view, gt, color, final_T, radii, loss_out, dL_dpix, lambda_dssim=0.2):
         s = rast.stream

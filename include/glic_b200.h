@@ -186,6 +186,22 @@ GLIC_API int glic_adam_update_packed(float* params, const float* grads, float* e
                                      uint32_t P, uint32_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * On-disk map.  Replaces GaussianModel::saveMap (gaussian.cpp:305-397, through tinyply.h:588-703):
+ * binary little-endian PLY, element vertex, float properties x y z | f_dc_0..2 | f_rest_0..3M-1 | opacity | scale_0..2 |
+ * rot_0..3; RAW parameters; f_rest channel-major.  The file is byte-identical to the reference's for the same tensors
+ * (pinned against the reference's own tinyply in tests/test_map_io.py).  All pointers are HOST pointers; f_dc is
+ * [P,1,3], f_rest [P,M,3] in the in-memory (coefficient-major) layout.  glic_ply_read* accept exactly this layout
+ * (comments allowed) and fail loudly on anything else.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_ply_bytes(uint32_t P, uint32_t M);
+GLIC_API int glic_ply_write(const char* path, uint32_t P, uint32_t M, const float* xyz, const float* f_dc, const float* f_rest,
+                            const float* opacity, const float* scale, const float* rotation);
+GLIC_API int glic_ply_write_packed(const char* path, uint32_t P, uint32_t M, const float* params_host);
+GLIC_API int glic_ply_read_header(const char* path, uint32_t* P, uint32_t* M, size_t* data_offset);
+GLIC_API int glic_ply_read(const char* path, uint32_t P, uint32_t M, float* xyz, float* f_dc, float* f_rest, float* opacity,
+                           float* scale, float* rotation);
+
+/* ---------------------------------------------------------------------------------------
  * Fused SSIM.  Replaces fusedssimCUDA / fusedssim_backwardCUDA (fused-ssim/ssim.cu:186-365).
  * img*: [B,CH,H,W] contiguous.  Partial-derivative maps may be NULL in forward (train = false).
  * ------------------------------------------------------------------------------------- */
