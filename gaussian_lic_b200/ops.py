@@ -145,6 +145,50 @@ def fused_ssim(img1, img2):
     return FusedSSIMMap.apply(SSIM_C1, SSIM_C2, img1, img2).mean()
 
 
+# ---- render() and the model getters it uses (rasterizer/renderer.cpp:21-88; gaussian.cpp:147-175) ------------------
+class GaussianParams:
+    """The six raw parameter tensors of GaussianModel with its activation getters (sigmoid / exp / normalize)."""
+
+    def __init__(self, xyz, features_dc, features_rest, opacity, scaling, rotation, sh_degree, lambda_erank=0.0):
+        self.xyz_, self.features_dc_, self.features_rest_ = xyz, features_dc, features_rest
+        self.opacity_, self.scaling_, self.rotation_ = opacity, scaling, rotation
+        self.sh_degree_, self.lambda_erank_ = int(sh_degree), float(lambda_erank)
+
+    def getXYZ(self):
+        return self.xyz_
+
+    def getOpacity(self):
+        return torch.sigmoid(self.opacity_)
+
+    def getScaling(self):
+        return torch.exp(self.scaling_)
+
+    def getRotation(self):
+        return torch.nn.functional.normalize(self.rotation_)
+
+    def getFeaturesDc(self):
+        return self.features_dc_
+
+    def getFeaturesRest(self):
+        return self.features_rest_
+
+
+def render(viewpoint_camera, pc, bg_color, no_color=False, scaling_modifier=1.0):
+    """renderer.cpp:21-88.  viewpoint_camera: mapping with W, H, tanfovx, tanfovy, lims[4] and DEVICE tensors view[16|4x4],
+    proj[16|4x4], campos[3] (column-major, as Camera stores the transposed matrices).  Returns the reference's tuple
+    (rendered_image, rendered_final_T, screenspace_points, radii > 0, radii)."""
+    xyz = pc.getXYZ()
+    screenspace_points = torch.zeros_like(xyz, requires_grad=True)
+    cam = viewpoint_camera
+    lims = [float(x) for x in cam["lims"]]
+    rs = GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], lims[0], lims[1], lims[2], lims[3],
+                                       bg_color, scaling_modifier, cam["view"].view(4, 4), cam["proj"].view(4, 4),
+                                       pc.sh_degree_, cam["campos"], False, False, no_color, pc.lambda_erank_)
+    rendered_image, radii, rendered_final_T = GaussianRasterizer(rs)(xyz, screenspace_points, pc.getOpacity(), pc.getFeaturesDc(),
+                                                                     pc.getFeaturesRest(), pc.getScaling(), pc.getRotation())
+    return rendered_image, rendered_final_T, screenspace_points, radii > 0, radii
+
+
 # ---- optimiser (optim_utils.h:69-137; gaussian.cpp:399-424) ---------------------------------------------
 class SparseGaussianAdam:
     """One tensor per group, visibility-masked, no bias correction, eps = 1e-15."""
