@@ -146,3 +146,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "glic_oracle" not in src, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/glic_b200.h must be consumable by a C compiler (no C++ or torch types in the signatures) and a C program must
+    link against libglic_b200.so and resolve every declared entry point."""
+    import subprocess
+    from gaussian_lic_b200 import capi
+    names = _declared()
+    src = tmp_path / "use.c"
+    body = "\n".join("    p[%d] = (fn)&%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "glic_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n    fn p[%d];\n%s\n'
+                   '    printf("%%d %%d\\n", glic_abi_version(), (int)(sizeof(p) / sizeof(p[0])));\n'
+                   '    glic_view v; v.width = 64; v.height = 48; (void)v;\n    return glic_geom_bytes(10) > 0 ? 0 : 1;\n}\n'
+                   % (len(names), body))
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libglic_b200.so", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["1", str(len(names))], (r.stdout, r.stderr)
