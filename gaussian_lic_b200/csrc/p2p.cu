@@ -139,19 +139,29 @@ int glic_p2p_open(const unsigned char* handle64, void** peer_ptr) {
 int glic_p2p_close(void* peer_ptr) { GLIC_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr)); return GLIC_OK; }
 int glic_p2p_free(void* dev_ptr) { GLIC_CUDA_TRY(cudaFree(dev_ptr)); return GLIC_OK; }
 
+// Rank r's share of the two-shot exchange, in 16-byte units: floats [lo4, hi4), visibility [vlo4, vhi4) (relative to the
+// visibility block at byte f_bytes); also the byte offsets of the visibility block and of the flag words.  The slices of the
+// `world` ranks partition both blocks exactly (tests/test_cabi.py), so every 16-byte unit is reduced by exactly one rank.
+int glic_p2p_slice(int rank, int world, size_t n_floats, size_t n_vis_bytes, size_t* out6) {
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || !out6) { set_error("p2p_slice: bad rank / world"); return GLIC_ERR_INVALID_ARGUMENT; }
+    const size_t f_bytes = (n_floats * 4 + 255) & ~size_t(255);
+    const size_t v_bytes = (n_vis_bytes + 255) & ~size_t(255);
+    const size_t f4 = f_bytes / 16, v4 = v_bytes / 16;
+    const size_t fper = (f4 + world - 1) / world, vper = (v4 + world - 1) / world;
+    out6[0] = std::min(f4, fper * rank); out6[1] = std::min(f4, fper * (rank + 1));
+    out6[2] = std::min(v4, vper * rank); out6[3] = std::min(v4, vper * (rank + 1));
+    out6[4] = f_bytes; out6[5] = f_bytes + v_bytes;
+    return GLIC_OK;
+}
+
 int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t n_floats, size_t n_vis_bytes, void* stream) {
     if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || !bufs_host) { set_error("p2p_allreduce: bad rank / world"); return GLIC_ERR_INVALID_ARGUMENT; }
     cudaStream_t s = (cudaStream_t)stream;
     PeerBufs pb;
     for (int q = 0; q < P2P_MAX_RANKS; ++q) pb.p[q] = q < world ? static_cast<char*>(bufs_host[q]) : nullptr;
-    const size_t f_bytes = (n_floats * 4 + 255) & ~size_t(255);
-    const size_t v_bytes = (n_vis_bytes + 255) & ~size_t(255);
-    const size_t flag_off = f_bytes + v_bytes;
-    // slices in 16-byte units, rank r takes [r*per, min((r+1)*per, total))
-    const size_t f4 = f_bytes / 16, v4 = v_bytes / 16;
-    const size_t fper = (f4 + world - 1) / world, vper = (v4 + world - 1) / world;
-    const size_t lo4 = std::min(f4, fper * rank), hi4 = std::min(f4, fper * (rank + 1));
-    const size_t vlo4 = std::min(v4, vper * rank), vhi4 = std::min(v4, vper * (rank + 1));
+    size_t sl[6];
+    glic_p2p_slice(rank, world, n_floats, n_vis_bytes, sl);
+    const size_t lo4 = sl[0], hi4 = sl[1], vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
     { StageTimer _t(GLIC_STAGE_ALLREDUCE, s);
       p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);         // every peer's gradients are complete
       GLIC_LAUNCH_CHECK();

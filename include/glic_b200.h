@@ -253,6 +253,7 @@ GLIC_API int glic_debug_image(int width, int height, const void* image_ws, uint3
  * glic_p2p_alloc is the one place this library allocates device memory: IPC needs a dedicated cudaMalloc block.
  * ------------------------------------------------------------------------------------- */
 GLIC_API size_t glic_p2p_buffer_bytes(size_t n_floats, size_t n_vis_bytes);
+GLIC_API int glic_p2p_slice(int rank, int world, size_t n_floats, size_t n_vis_bytes, size_t* out6_host);
 GLIC_API int glic_p2p_alloc(size_t bytes, void** dev_ptr_host, unsigned char* handle64_host);
 GLIC_API int glic_p2p_open(const unsigned char* handle64_host, void** peer_ptr_host);
 GLIC_API int glic_p2p_close(void* peer_ptr);

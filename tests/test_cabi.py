@@ -126,6 +126,32 @@ def test_packed_layout_and_exchange_sizes():
     assert lib.glic_p2p_alloc(1024, None, None) == -1
 
 
+def test_p2p_slices_partition_the_payload():
+    """Every 16-byte unit of the gradient block and of the visibility block belongs to exactly one rank's slice."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from gaussian_lic_b200 import capi
+    lib = capi.lib
+
+    @hyp.given(st.integers(0, 3_000_000), st.integers(0, 70_000), st.integers(1, 8))
+    @hyp.settings(max_examples=300, deadline=None)
+    def prop(n_floats, n_vis, world):
+        out = (C.c_size_t * 6)()
+        f_end = v_end = 0
+        for r in range(world):
+            assert lib.glic_p2p_slice(r, world, n_floats, n_vis, out) == 0
+            lo, hi, vlo, vhi, f_bytes, flag_off = [int(x) for x in out]
+            assert lo == f_end and hi >= lo and vlo == v_end and vhi >= vlo          # contiguous, in rank order
+            f_end, v_end = hi, vhi
+            assert f_bytes % 256 == 0 and f_bytes >= n_floats * 4 and flag_off % 256 == 0 and flag_off - f_bytes >= n_vis
+        assert f_end * 16 == f_bytes and v_end * 16 == flag_off - f_bytes            # ... and complete
+        assert flag_off + 256 == lib.glic_p2p_buffer_bytes(n_floats, n_vis)
+
+    prop()
+    out = (C.c_size_t * 6)()
+    assert lib.glic_p2p_slice(3, 3, 10, 10, out) == -1 and lib.glic_p2p_slice(0, 9, 10, 10, out) == -1
+
+
 def test_package_fails_loudly_without_library(tmp_path, monkeypatch):
     """No silent CPU/PyTorch fallback: a missing .so is an ImportError."""
     import importlib
