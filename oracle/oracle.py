@@ -198,6 +198,28 @@ class Oracle:
         self.lib.glic_oracle_activations_backward(C.c_int(op.shape[0]), _ptr(op), _ptr(sc), _ptr(rr), _ptr(g1), _ptr(g2), _ptr(g3))
         return g1, g2, g3
 
+    def extend_select(self, points, depth_rsp, R_cw, t_cw, fx, fy, cx, cy, W, H, final_T):
+        """Indices (ascending) of the LiDAR points extend() turns into Gaussians (gaussian.cpp:499-607)."""
+        p, d = self._a(points), self._a(depth_rsp).reshape(-1)
+        R, t, T = self._a(R_cw), self._a(t_cw).reshape(-1), self._a(final_T)
+        keep = np.zeros(max(p.shape[0], 1), np.int32)
+        self.lib.glic_oracle_extend_select.restype = C.c_int
+        m = self.lib.glic_oracle_extend_select(C.c_int(p.shape[0]), _ptr(p), _ptr(d), _ptr(R), _ptr(t), self.real(fx), self.real(fy),
+                                               self.real(cx), self.real(cy), C.c_int(W), C.c_int(H), _ptr(T), _ptr(keep))
+        return keep[:m].copy()
+
+    def extend_init(self, keep, points, colors, depth_rsp, scaling_scale, fx, fy):
+        """Initial raw parameters of the inserted Gaussians (gaussian.cpp:610-631)."""
+        k = np.ascontiguousarray(keep, np.int32)
+        m = k.shape[0]
+        p, c, d = self._a(points), self._a(colors), self._a(depth_rsp).reshape(-1)
+        out = dict(xyz=np.zeros((m, 3), self.dtype), f_dc=np.zeros((m, 3), self.dtype), log_scale=np.zeros((m, 3), self.dtype),
+                   rot=np.zeros((m, 4), self.dtype), opacity_logit=np.zeros(m, self.dtype))
+        self.lib.glic_oracle_extend_init(C.c_int(m), _ptr(k), _ptr(p), _ptr(c), _ptr(d), self.real(scaling_scale), self.real(fx),
+                                         self.real(fy), _ptr(out["xyz"]), _ptr(out["f_dc"]), _ptr(out["log_scale"]), _ptr(out["rot"]),
+                                         _ptr(out["opacity_logit"]))
+        return out
+
     def knn(self, pts):
         p = self._a(pts)
         out = np.zeros(p.shape[0], self.dtype)

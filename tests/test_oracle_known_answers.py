@@ -122,3 +122,53 @@ def test_camera_restatements_agree(oracle32):
         p = np.array([0, 0, 10.0, 1.0])
         h = a["proj"].reshape(4, 4).T @ p
         assert abs(h[0] / h[3]) < 1e-5 and abs(h[1] / h[3]) < 1e-5 and h[3] > 0
+
+
+def test_extend_selection_and_initialisation():
+    """extend() (gaussian.cpp:499-638) restated for the GPU version of the next round: per-pixel nearest-point de-duplication
+    over ALL points, then the in-image / positive-depth / alpha < 0.99 filter, then the initial parameters."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    o = Oracle(np.float64)
+    W, H, fx, fy, cx, cy = 8, 6, 4.0, 4.0, 4.0, 3.0
+    R, t = np.eye(3), np.zeros(3)
+    T = np.ones((H, W))                       # alpha = 0 everywhere ...
+    T[3, 5] = 0.005                           # ... except one saturated pixel (alpha 0.995 >= 0.99)
+    pts = np.array([[0.0, 0.0, 2.0],          # 0: pixel (4,3), depth 2
+                    [0.05, 0.05, 1.0],        # 1: pixel (4,3) too, nearer -> wins over 0
+                    [0.1, 0.1, 1.0],          # 2: pixel (4,3), same depth as 1 but later index -> loses the tie
+                    [0.5, 0.0, 2.0],          # 3: pixel (5,3): saturated -> dropped
+                    [-10.0, 0.0, 1.0],        # 4: pixel (-36,3): outside -> dropped
+                    [1.0, 0.5, 4.0],          # 5: pixel (5,3)? (1*4/4+4, .5*4/4+3) = (5,3) farther than 3 -> loses; 3 itself is dropped later
+                    [-0.5, -0.5, 2.0],        # 6: pixel (3,2) kept
+                    [0.6, 0.6, -2.0],         # 7: behind the camera: pixel (2,1), still takes part (reference quirk) and is kept
+                    [-0.5, -0.5, 2.5]])       # 8: pixel (3,2), farther than 6 -> loses
+    rsp = np.array([1, 1, 1, 1, 1, 1, 1, 1, 1.0])
+    keep = o.extend_select(pts, rsp, R, t, fx, fy, cx, cy, W, H, T)
+    assert keep.tolist() == [1, 6, 7]
+    rsp[6] = 0.0                              # depth_in_rsp_frame must be > 0
+    assert o.extend_select(pts, rsp, R, t, fx, fy, cx, cy, W, H, T).tolist() == [1, 7]
+    # a rigid transform is applied before projecting: shifting the camera by +1 in x moves every pixel by fx/z
+    keep2 = o.extend_select(pts + np.array([1.0, 0, 0]), np.ones(9), R, np.array([-1.0, 0, 0]), fx, fy, cx, cy, W, H, T)
+    assert keep2.tolist() == [1, 6, 7]
+    cols = np.linspace(0, 1, 27).reshape(9, 3)
+    init = o.extend_init(keep, pts, cols, np.arange(1, 10.0), 0.7, fx, 6.0)
+    np.testing.assert_allclose(init["xyz"], pts[keep])
+    np.testing.assert_allclose(init["f_dc"], (cols[keep] - 0.5) / 0.28209479177387814, rtol=1e-14)
+    np.testing.assert_allclose(init["log_scale"], np.log(0.7 * np.arange(1, 10.0)[keep] / 5.0)[:, None].repeat(3, 1), rtol=1e-14)
+    assert np.array_equal(init["rot"], np.tile([1.0, 0, 0, 0], (3, 1)))
+    np.testing.assert_allclose(init["opacity_logit"], np.log(0.1 / 0.9), rtol=1e-14)
+    # random cross-check against a dictionary restatement of the reference's loop
+    rng = np.random.default_rng(0)
+    n = 400
+    p = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(0.5, 6, n)]
+    Tm = rng.uniform(0, 0.05, (H, W)); Tm[rng.uniform(size=(H, W)) < 0.6] = 1.0
+    d = rng.uniform(-0.2, 3, n)
+    keep = o.extend_select(p, d, R, t, fx, fy, cx, cy, W, H, Tm)
+    best = {}
+    for i in range(n):
+        key = (int(np.floor(p[i, 0] * fx / p[i, 2] + cx)), int(np.floor(p[i, 1] * fy / p[i, 2] + cy)))
+        if key not in best or p[i, 2] < best[key][1]:
+            best[key] = (i, p[i, 2])
+    want = sorted(i for (x, y), (i, _) in best.items() if 0 <= x < W and 0 <= y < H and d[i] > 0 and 1 - Tm[y, x] < 0.99)
+    assert keep.tolist() == want
