@@ -58,6 +58,9 @@ def _load():
         "glic_fused_ssim_backward": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_l1_ssim_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp]),
         "glic_knn_mean_dist2": (i32, [i32, vp, vp, vp, sz, vp]),
+        "glic_extend_bytes": (sz, [i32, i32, i32]),
+        "glic_extend": (i32, [i32, vp, vp, vp, C.POINTER(f32), C.POINTER(f32), f32, f32, f32, f32, i32, i32, vp, f32, vp, sz, vp, vp,
+                              vp, vp, vp, vp, C.POINTER(i32), vp]),
         "glic_ply_bytes": (sz, [u32, u32]),
         "glic_ply_write": (i32, [C.c_char_p, u32, u32, vp, vp, vp, vp, vp, vp]),
         "glic_ply_write_packed": (i32, [C.c_char_p, u32, u32, vp]),

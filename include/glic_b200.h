@@ -186,6 +186,19 @@ GLIC_API int glic_adam_update_packed(float* params, const float* grads, float* e
                                      uint32_t P, uint32_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * EXPERIMENTAL -- extend() on the GPU (gaussian.cpp:499-638).  Written at the end of round 1, compiled
+ * but NOT YET EXECUTED on a GPU (its parity test runs only with GLIC_EXPERIMENTAL=1); the CPU oracle
+ * (its extend restatement) is what it will be checked against.  Device pointers except R_cw_host[9]
+ * (row-major), t_cw_host[3] and count_host.  final_T comes from a no_color forward of the newest view.  Outputs hold the
+ * kept points in ascending index order (the reference's order is unordered_map order, i.e. unspecified).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_extend_bytes(int n, int width, int height);
+GLIC_API int glic_extend(int n, const float* points, const float* colors, const float* depth_rsp, const float* R_cw_host,
+                         const float* t_cw_host, float fx, float fy, float cx, float cy, int width, int height,
+                         const float* final_T, float scaling_scale, void* ws, size_t ws_bytes, int* keep_idx, float* xyz,
+                         float* f_dc, float* log_scale, float* rot, float* opacity_logit, int* count_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * On-disk map.  Replaces GaussianModel::saveMap (gaussian.cpp:305-397, through tinyply.h:588-703):
  * binary little-endian PLY, element vertex, float properties x y z | f_dc_0..2 | f_rest_0..3M-1 | opacity | scale_0..2 |
  * rot_0..3; RAW parameters; f_rest channel-major.  The file is byte-identical to the reference's for the same tensors
