@@ -72,6 +72,8 @@ def _load():
         "glic_activations_backward": (i32, [i32, vp, vp, vp, vp, vp, vp, vp]),
         "glic_adam_update_packed": (i32, [vp, vp, vp, vp, vp, C.POINTER(f32), f32, f32, f32, u32, u32, vp]),
         "glic_p2p_buffer_bytes": (sz, [sz, sz]),
+        "glic_p2p_model_bytes": (sz, [sz, sz]),
+        "glic_p2p_reduce_adam": (i32, [i32, i32, C.POINTER(vp), u32, u32, vp, vp, C.POINTER(f32), f32, f32, f32, vp]),
         "glic_p2p_slice": (i32, [i32, i32, sz, sz, C.POINTER(sz)]),
         "glic_p2p_alloc": (i32, [sz, C.POINTER(vp), C.c_char_p]),
         "glic_p2p_open": (i32, [C.c_char_p, C.POINTER(vp)]),

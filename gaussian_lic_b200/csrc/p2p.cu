@@ -104,6 +104,56 @@ void launch_reduce(const PeerBufs& pb, size_t lo4, size_t hi4, size_t vis_off, s
     p2p_reduce_kernel<WORLD, UNROLL><<<blocks, 512, 0, s>>>(pb, lo4, hi4, vis_off, vlo4, vhi4, 1.0f / (float)WORLD);
 }
 
+// ---- EXPERIMENTAL: reduce-scatter -> Adam on the local slice -> all-gather of PARAMETERS ------------------
+// Written at the end of round 1, compiled but not yet executed (opt-in test tests/test_gpu_p2p_adam.py).  Same NVLink
+// bytes as the all-reduce (gradients in, parameters out), Adam's HBM traffic and its moment buffers divided by `world`.
+struct P2PLayout {
+    size_t begin[6], end[6];
+    uint32_t k[6];
+    float lr[6];
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(256)
+p2p_reduce_adam_kernel(PeerBufs bufs, int rank, size_t lo4, size_t hi4, size_t vis_off, size_t params_off,
+                       float4* __restrict__ exp_avg, float4* __restrict__ exp_avg_sq, P2PLayout L, size_t total, float b1, float b2,
+                       float eps) {
+    const float inv = 1.0f / (float)WORLD;
+    const uint8_t* __restrict__ visible = reinterpret_cast<const uint8_t*>(bufs.p[rank] + vis_off);   // union, reduced just before
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+        float4 g4[WORLD];
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) g4[q] = __ldcv(reinterpret_cast<const float4*>(bufs.p[q]) + i);
+        float4 acc = g4[0];
+#pragma unroll
+        for (int q = 1; q < WORLD; ++q) { acc.x += g4[q].x; acc.y += g4[q].y; acc.z += g4[q].z; acc.w += g4[q].w; }
+        float g[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+        float4 p4 = reinterpret_cast<const float4*>(bufs.p[rank] + params_off)[i];
+        float4 m4 = exp_avg[i], v4 = exp_avg_sq[i];
+        float p[4] = {p4.x, p4.y, p4.z, p4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const size_t j = 4 * i + c;
+            if (j >= total) continue;
+            int grp = 0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) grp += j >= L.end[q];
+            if (!visible[(j - L.begin[grp]) / L.k[grp]]) continue;
+            // adam_kernel's arithmetic (adamUpdateCUDA, adam.cu:9-38), element for element
+            const float mm = b1 * m[c] + (1.0f - b1) * g[c];
+            const float vv = b2 * v[c] + (1.0f - b2) * g[c] * g[c];
+            p[c] += -L.lr[grp] * mm / (sqrtf(vv) + eps);
+            m[c] = mm; v[c] = vv;
+        }
+        exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
+        exp_avg_sq[i] = make_float4(v[0], v[1], v[2], v[3]);
+        const float4 out = make_float4(p[0], p[1], p[2], p[3]);
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) reinterpret_cast<float4*>(bufs.p[q] + params_off)[i] = out;
+    }
+}
+
 }  // namespace
 }  // namespace glic
 
@@ -176,6 +226,50 @@ int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t 
 #undef GLIC_P2P_CASE
       GLIC_LAUNCH_CHECK();
       p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);      // every slice has been written everywhere
+      GLIC_LAUNCH_CHECK(); }
+    return GLIC_OK;
+}
+
+// Buffer of the fused variant: gradients | visibility | flags (as glic_p2p_buffer_bytes) | parameters.
+size_t glic_p2p_model_bytes(size_t n_floats, size_t n_vis_bytes) {
+    return glic_p2p_buffer_bytes(n_floats, n_vis_bytes) + ((n_floats * 4 + 255) & ~size_t(255));
+}
+
+// EXPERIMENTAL (see above).  bufs_host[q]: rank q's glic_p2p_model_bytes block.  exp_avg / exp_avg_sq: LOCAL, n_floats each
+// (only this rank's slice is ever touched).  After the call every rank's parameter block holds the updated model.
+int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P, uint32_t M, float* exp_avg, float* exp_avg_sq,
+                         const float* lr6_host, float b1, float b2, float eps, void* stream) {
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || !bufs_host || !exp_avg || !exp_avg_sq || !lr6_host) {
+        set_error("p2p_reduce_adam: bad arguments"); return GLIC_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerBufs pb;
+    for (int q = 0; q < P2P_MAX_RANKS; ++q) pb.p[q] = q < world ? static_cast<char*>(bufs_host[q]) : nullptr;
+    P2PLayout L;
+    const uint32_t k[6] = {4, 3, 3, 1, 3, 3 * M};
+    size_t off = 0;
+    for (int q = 0; q < 6; ++q) { L.begin[q] = off; L.k[q] = k[q] ? k[q] : 1; L.lr[q] = lr6_host[q]; off += (size_t)P * k[q]; L.end[q] = off; }
+    const size_t n_floats = off;
+    size_t sl[6];
+    glic_p2p_slice(rank, world, n_floats, (size_t)P, sl);
+    const size_t lo4 = sl[0], hi4 = sl[1], vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
+    const size_t params_off = flag_off + 256;
+    { StageTimer _t(GLIC_STAGE_ALLREDUCE, s);
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // every peer's gradients and visibility are complete
+      GLIC_LAUNCH_CHECK();
+#define GLIC_P2P_VIS(WD) case WD: launch_reduce<WD, 1>(pb, 0, 0, f_bytes, vlo4, vhi4, 2, s); break;
+      switch (world) { GLIC_P2P_VIS(1) GLIC_P2P_VIS(2) GLIC_P2P_VIS(3) GLIC_P2P_VIS(4) GLIC_P2P_VIS(5) GLIC_P2P_VIS(6) GLIC_P2P_VIS(7) GLIC_P2P_VIS(8) }
+#undef GLIC_P2P_VIS
+      GLIC_LAUNCH_CHECK();
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // the visibility union is everywhere
+      GLIC_LAUNCH_CHECK();
+      const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((hi4 - lo4 + 255) / 256, (size_t)148 * 4));
+#define GLIC_P2P_ADAM(WD) case WD: p2p_reduce_adam_kernel<WD><<<blocks, 256, 0, s>>>(pb, rank, lo4, hi4, f_bytes, params_off, \
+          reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), L, n_floats, b1, b2, eps); break;
+      switch (world) { GLIC_P2P_ADAM(1) GLIC_P2P_ADAM(2) GLIC_P2P_ADAM(3) GLIC_P2P_ADAM(4) GLIC_P2P_ADAM(5) GLIC_P2P_ADAM(6) GLIC_P2P_ADAM(7) GLIC_P2P_ADAM(8) }
+#undef GLIC_P2P_ADAM
+      GLIC_LAUNCH_CHECK();
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // every parameter slice has been written everywhere
       GLIC_LAUNCH_CHECK(); }
     return GLIC_OK;
 }

@@ -94,7 +94,7 @@ class P2PGradAllReduce:
             raise ValueError("P2PGradAllReduce supports up to 8 ranks (one NVSwitch domain)")
         self.n_floats = int(P) * PackedGrads.floats_per_gaussian(M)
         self.n_vis = int(P)
-        nbytes = int(self.lib.glic_p2p_buffer_bytes(self.n_floats, self.n_vis))
+        nbytes = self._nbytes()
         # Every phase that can fail locally (allocation, IPC export, IPC import) is followed by an exchange of the outcome,
         # so that all ranks raise together instead of one rank leaving the others inside a collective.
         own, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -140,6 +140,9 @@ class P2PGradAllReduce:
         if self.world > 1:
             dist.barrier(group=group)            # every peer has mapped every buffer before first use
 
+    def _nbytes(self):
+        return int(self.lib.glic_p2p_buffer_bytes(self.n_floats, self.n_vis))
+
     @property
     def grads(self):
         return self.packed.grads
@@ -167,6 +170,38 @@ class P2PGradAllReduce:
         if getattr(self, "_own", None):
             self.lib.glic_p2p_free(self._C.c_void_p(self._own))
         self._own = None
+
+
+class P2PModelExchange(P2PGradAllReduce):
+    """EXPERIMENTAL (never run on a GPU yet; opt-in test tests/test_gpu_p2p_adam.py): the fused form of the exchange.
+    The mapped block additionally holds the PARAMETERS (packed layout); `step(radii)` reduce-scatters the gradients,
+    applies the visibility-masked Adam to this rank's slice only and all-gathers the updated parameters into every
+    replica (csrc/p2p.cu, glic_p2p_reduce_adam).  The moment buffers are touched on the local slice only."""
+
+    def __init__(self, P, M, device, lr6, group=None, betas=(0.9, 0.999), eps=1e-15):
+        super().__init__(P, M, device, group=group)
+        C = self._C
+        f_bytes = (self.n_floats * 4 + 255) // 256 * 256
+        v_bytes = (self.n_vis + 255) // 256 * 256
+        off = f_bytes + v_bytes + 256
+        self.params = self._raw[off:off + self.n_floats * 4].view(torch.float32)
+        self.exp_avg = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
+        self.P_, self.M_ = int(P), int(M)
+        self.lr6 = (C.c_float * 6)(*[float(x) for x in lr6])
+        self.b1, self.b2, self.eps = float(betas[0]), float(betas[1]), float(eps)
+
+    def _nbytes(self):
+        return int(self.lib.glic_p2p_model_bytes(self.n_floats, self.n_vis))
+
+    def step(self, radii):
+        pk = self.packed
+        torch.gt(radii[:pk.P], 0, out=pk.visible.view(torch.bool))
+        stream = torch.cuda.current_stream().cuda_stream
+        self._capi.check(self.lib.glic_p2p_reduce_adam(self.rank, self.world, self._peers, self.P_, self.M_,
+                                                       self._capi.ptr(self.exp_avg), self._capi.ptr(self.exp_avg_sq), self.lr6,
+                                                       self.b1, self.b2, self.eps, self._C.c_void_p(stream)), "glic_p2p_reduce_adam")
+        return self.params
 
 
 def shard_views(n_views, rank, world):

@@ -274,6 +274,14 @@ GLIC_API int glic_p2p_free(void* dev_ptr);
 GLIC_API int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t n_floats, size_t n_vis_bytes,
                                      void* stream);
 
+/* EXPERIMENTAL -- fused exchange + optimiser: reduce-scatter of the gradients, visibility-masked Adam on the local slice,
+ * all-gather of the updated PARAMETERS, in one kernel over peer memory (same NVLink bytes as the all-reduce, Adam traffic
+ * and moment buffers / world).  Buffer = glic_p2p_model_bytes: gradients | visibility | flags | parameters (packed layout).
+ * Written at the end of round 1, compiled but NOT YET EXECUTED (opt-in test, GLIC_EXPERIMENTAL=1). */
+GLIC_API size_t glic_p2p_model_bytes(size_t n_floats, size_t n_vis_bytes);
+GLIC_API int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P, uint32_t M, float* exp_avg,
+                                  float* exp_avg_sq, const float* lr6_host, float b1, float b2, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Stage timing (cudaEvent pairs recorded on the launching stream around each stage; off by
  * default).  glic_profile_enable(1) starts recording and resets the accumulators;
