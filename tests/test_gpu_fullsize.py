@@ -6,7 +6,6 @@ and (b) size-independent properties of the binning / blend / backward: the tile 
 of exactly the pairs the per-Gaussian tile counts promise, ranges partition it, contributor counts are consistent,
 two runs are bit-identical, and the backward is linear in dL/dpixel.
 """
-import numpy as np
 import pytest
 
 from helpers import grad_close

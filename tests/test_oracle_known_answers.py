@@ -1,5 +1,4 @@
 """Known-answer and property tests of the CPU oracle -- no GPU needed."""
-import math
 
 import numpy as np
 import pytest
