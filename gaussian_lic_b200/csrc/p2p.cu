@@ -235,8 +235,8 @@ size_t glic_p2p_model_bytes(size_t n_floats, size_t n_vis_bytes) {
     return glic_p2p_buffer_bytes(n_floats, n_vis_bytes) + ((n_floats * 4 + 255) & ~size_t(255));
 }
 
-// EXPERIMENTAL (see above).  bufs_host[q]: rank q's glic_p2p_model_bytes block.  exp_avg / exp_avg_sq: LOCAL, n_floats each
-// (only this rank's slice is ever touched).  After the call every rank's parameter block holds the updated model.
+// EXPERIMENTAL (see above).  bufs_host[q]: rank q's glic_p2p_model_bytes block.  exp_avg / exp_avg_sq: LOCAL, 16-byte aligned,
+// n_floats rounded up to a multiple of 4 floats each (only this rank's slice is ever touched).  After the call every rank's parameter block holds the updated model.
 int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P, uint32_t M, float* exp_avg, float* exp_avg_sq,
                          const float* lr6_host, float b1, float b2, float eps, void* stream) {
     if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || !bufs_host || !exp_avg || !exp_avg_sq || !lr6_host) {
@@ -252,7 +252,9 @@ int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P
     const size_t n_floats = off;
     size_t sl[6];
     glic_p2p_slice(rank, world, n_floats, (size_t)P, sl);
-    const size_t lo4 = sl[0], hi4 = sl[1], vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
+    // float4 units past the last real float belong to the padding: never touched (the moment buffers are not padded to 256 B)
+    const size_t used4 = (n_floats + 3) / 4;
+    const size_t lo4 = std::min(sl[0], used4), hi4 = std::min(sl[1], used4), vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
     const size_t params_off = flag_off + 256;
     { StageTimer _t(GLIC_STAGE_ALLREDUCE, s);
       p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // every peer's gradients and visibility are complete

@@ -185,8 +185,9 @@ class P2PModelExchange(P2PGradAllReduce):
         v_bytes = (self.n_vis + 255) // 256 * 256
         off = f_bytes + v_bytes + 256
         self.params = self._raw[off:off + self.n_floats * 4].view(torch.float32)
-        self.exp_avg = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
-        self.exp_avg_sq = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
+        padded = (self.n_floats + 63) // 64 * 64                      # the kernel works in float4 units
+        self.exp_avg = torch.zeros(padded, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(padded, dtype=torch.float32, device=device)
         self.P_, self.M_ = int(P), int(M)
         self.lr6 = (C.c_float * 6)(*[float(x) for x in lr6])
         self.b1, self.b2, self.eps = float(betas[0]), float(betas[1]), float(eps)
