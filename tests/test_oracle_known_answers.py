@@ -171,3 +171,33 @@ def test_extend_selection_and_initialisation():
             best[key] = (i, p[i, 2])
     want = sorted(i for (x, y), (i, _) in best.items() if 0 <= x < W and 0 <= y < H and d[i] > 0 and 1 - Tm[y, x] < 0.99)
     assert keep.tolist() == want
+
+
+def test_activation_oracle_matches_the_reference_ops_on_cpu():
+    """The reference's getters ARE torch ops (gaussian.cpp:147-175: torch::sigmoid, torch::exp, functional::normalize) and
+    their backward is autograd's: run exactly those on the CPU and pin the oracle's restatement to them."""
+    import numpy as np
+    import pytest
+    torch = pytest.importorskip("torch")
+    from oracle.oracle import Oracle
+    o = Oracle(np.float32)
+    rng = np.random.default_rng(8)
+    P = 2000
+    a = rng.normal(0, 2, P).astype(np.float32)
+    b = rng.normal(-4, 0.6, (P, 3)).astype(np.float32)
+    c = rng.normal(0, 1, (P, 4)).astype(np.float32)
+    w1, w2, w3 = (rng.normal(size=s).astype(np.float32) for s in ((P,), (P, 3), (P, 4)))
+    ta, tb, tc = (torch.tensor(x, requires_grad=True) for x in (a, b, c))
+    top, tsc, trot = torch.sigmoid(ta), torch.exp(tb), torch.nn.functional.normalize(tc)
+    (top * torch.tensor(w1)).sum().backward()
+    (tsc * torch.tensor(w2)).sum().backward()
+    (trot * torch.tensor(w3)).sum().backward()
+    op, sc, rot = o.activations(a, b, c)
+    np.testing.assert_allclose(op, top.detach().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(sc, tsc.detach().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(rot, trot.detach().numpy(), rtol=2e-6, atol=1e-7)
+    g1, g2, g3 = o.activations_backward(op, sc, c, w1, w2, w3)
+    np.testing.assert_allclose(g1, ta.grad.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(g2, tb.grad.numpy(), rtol=1e-5)
+    scale = np.abs(tc.grad.numpy()).max()
+    assert np.abs(g3 - tc.grad.numpy()).max() <= 1e-5 * scale
