@@ -201,3 +201,30 @@ def test_activation_oracle_matches_the_reference_ops_on_cpu():
     np.testing.assert_allclose(g2, tb.grad.numpy(), rtol=1e-5)
     scale = np.abs(tc.grad.numpy()).max()
     assert np.abs(g3 - tc.grad.numpy()).max() <= 1e-5 * scale
+
+
+def test_ssim_oracle_matches_the_conv2d_formulation():
+    """loss_utils.h:52-127 (`ssim`, the evaluation metric) is the textbook SSIM written with grouped conv2d; the fused kernel
+    (and its oracle restatement, A.9) must produce the same map.  Run the conv2d formulation with torch on the CPU."""
+    import numpy as np
+    import pytest
+    torch = pytest.importorskip("torch")
+    from oracle.oracle import Oracle
+    o = Oracle(np.float32)
+    rng = np.random.default_rng(2)
+    CH, H, W = 3, 37, 53
+    a = rng.uniform(0, 1, (CH, H, W)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.1, a.shape), 0, 1).astype(np.float32)
+    x = torch.arange(11, dtype=torch.float32) - 5
+    g = torch.exp(-(x * x) / (2 * 1.5 * 1.5))
+    g = g / g.sum()
+    win = (g[:, None] @ g[None, :]).expand(CH, 1, 11, 11).contiguous()
+    conv = lambda t: torch.nn.functional.conv2d(t, win, padding=5, groups=CH)
+    i1, i2 = torch.tensor(a)[None], torch.tensor(b)[None]
+    mu1, mu2 = conv(i1), conv(i2)
+    s1, s2, s12 = conv(i1 * i1) - mu1 * mu1, conv(i2 * i2) - mu2 * mu2, conv(i1 * i2) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ref_map = ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))
+    m, _, _, _ = o.ssim(a[None], b[None], train=False)
+    np.testing.assert_allclose(m[0], ref_map[0].numpy(), rtol=0, atol=3e-5)
+    assert abs(float(m.mean()) - float(ref_map.mean())) < 2e-6
