@@ -228,3 +228,35 @@ def test_ssim_oracle_matches_the_conv2d_formulation():
     m, _, _, _ = o.ssim(a[None], b[None], train=False)
     np.testing.assert_allclose(m[0], ref_map[0].numpy(), rtol=0, atol=3e-5)
     assert abs(float(m.mean()) - float(ref_map.mean())) < 2e-6
+
+
+def test_photometric_loss_oracle_matches_torch_autograd():
+    """gaussian.cpp:692-697: loss = (1 - 0.2) * l1_loss + 0.2 * (1 - fused_ssim).  Value and dL/dimage of the oracle against torch
+    autograd through the conv2d SSIM and torch::abs(...).mean() on the CPU."""
+    import numpy as np
+    import pytest
+    torch = pytest.importorskip("torch")
+    from oracle.oracle import Oracle
+    o = Oracle(np.float32)
+    rng = np.random.default_rng(4)
+    CH, H, W = 3, 40, 56
+    a = rng.uniform(0, 1, (CH, H, W)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.15, a.shape), 0, 1).astype(np.float32)
+    x = torch.arange(11, dtype=torch.float64) - 5
+    g = torch.exp(-(x * x) / (2 * 1.5 * 1.5))
+    g = g / g.sum()
+    win = (g[:, None] @ g[None, :]).expand(CH, 1, 11, 11).contiguous()
+    conv = lambda t: torch.nn.functional.conv2d(t, win, padding=5, groups=CH)
+    i1 = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    i2 = torch.tensor(b, dtype=torch.float64)
+    u1, u2 = i1[None], i2[None]
+    mu1, mu2 = conv(u1), conv(u2)
+    s1, s2, s12 = conv(u1 * u1) - mu1 * mu1, conv(u2 * u2) - mu2 * mu2, conv(u1 * u2) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim = (((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))).mean()
+    loss = 0.8 * (i1 - i2).abs().mean() + 0.2 * (1 - ssim)
+    loss.backward()
+    L, dl = o.loss(a, b, 0.2)
+    assert abs(L - float(loss.detach())) < 2e-6
+    ref = i1.grad.numpy()
+    assert np.abs(dl - ref).max() <= 2e-4 * np.abs(ref).max()
