@@ -80,6 +80,7 @@ def _load():
         "glic_p2p_close": (i32, [vp]),
         "glic_p2p_free": (i32, [vp]),
         "glic_p2p_allreduce_mean": (i32, [i32, i32, C.POINTER(vp), sz, sz, vp]),
+        "glic_p2p_check": (i32, [vp, sz, sz, vp]),
         "glic_debug_geom": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_debug_binning": (i32, [i32, vp, i64, i64, vp, vp, vp, vp]),
         "glic_debug_image": (i32, [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp]),

@@ -4,6 +4,7 @@
 // SimpleKNN::knn (simple-knn/simple_knn.cu:45-221).  The knn path reuses this library's own
 // onesweep sort (no CUB / Thrust, no cudaMalloc, no host round trips for min/max).
 #include "common.cuh"
+#include "adam_math.cuh"
 #include <algorithm>
 #include <cfloat>
 
@@ -19,11 +20,9 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
     const size_t total = (size_t)N * M;
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (size_t)gridDim.x * blockDim.x) {
         if (!visible[j / M]) continue;
-        const float g = grad[j];
-        const float m = b1 * exp_avg[j] + (1.0f - b1) * g;
-        const float v = b2 * exp_avg_sq[j] + (1.0f - b2) * g * g;
-        const float step = -lr * m / (sqrtf(v) + eps);
-        param[j] += step;
+        float p = param[j], m = exp_avg[j], v = exp_avg_sq[j];
+        adam_element(p, m, v, grad[j], lr, b1, b2, eps);
+        param[j] = p;
         exp_avg[j] = m;
         exp_avg_sq[j] = v;
     }

@@ -31,6 +31,7 @@ __device__ __forceinline__ bool extend_pixel(const ExtendCam& c, const float* __
 }
 
 __device__ __forceinline__ unsigned int orderable(float f) {       // monotone float -> uint (negative depths included)
+    f = __fadd_rn(f, 0.0f);                                        // -0.0f -> +0.0f: the reference's float `<` treats them as equal
     const unsigned int b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }

@@ -9,6 +9,7 @@
 // the gradient buffer the backward just wrote, and the visibility-masked Adam of all six groups is a single launch
 // that consumes that buffer (and, multi-GPU, exactly the bytes the exchange step just reduced).
 #include "common.cuh"
+#include "adam_math.cuh"
 #include <algorithm>
 
 namespace glic {
@@ -74,12 +75,9 @@ adam_packed_kernel(float* __restrict__ param, const float* __restrict__ grad, fl
         for (int q = 0; q < 5; ++q) grp += j >= L.end[q];
         const size_t gaussian = (j - L.begin[grp]) / L.k[grp];
         if (!visible[gaussian]) continue;
-        const float lr = L.lr[grp];
-        const float g = grad[j];
-        const float m = b1 * exp_avg[j] + (1.0f - b1) * g;
-        const float v = b2 * exp_avg_sq[j] + (1.0f - b2) * g * g;
-        const float step = -lr * m / (sqrtf(v) + eps);
-        param[j] += step;
+        float p = param[j], m = exp_avg[j], v = exp_avg_sq[j];
+        adam_element(p, m, v, grad[j], L.lr[grp], b1, b2, eps);
+        param[j] = p;
         exp_avg[j] = m;
         exp_avg_sq[j] = v;
     }

@@ -10,6 +10,7 @@
 // the peers' backward kernels and against their readers.  Bytes over NVLink per rank: 2*(N-1)/N of the
 // payload, the minimum for an all-reduce.
 #include "common.cuh"
+#include "adam_math.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -31,26 +32,44 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Flag block (256 B at flag_off of every rank's buffer): words [0, 8) = "peer q reached epoch e" (written by peer q),
+// word 8 = this rank's epoch counter, word 9 = sticky error word (1 = a barrier timed out).
+constexpr int P2P_EPOCH_WORD = P2P_MAX_RANKS;
+constexpr int P2P_ERROR_WORD = P2P_MAX_RANKS + 1;
+
 // Thread q tells peer q "rank `rank` reached epoch e", then waits until peer q has told us the same.
-// The epoch lives in the rank's own flag block (word P2P_MAX_RANKS) and advances by one per barrier, so the
-// launch carries no per-call argument and the whole exchange can sit inside a replayed CUDA graph.
-__global__ void p2p_barrier_kernel(PeerBufs bufs, int rank, int world, size_t flag_off) {
+// The epoch lives in the rank's own flag block and advances by one per barrier, so the launch carries no per-call
+// argument and the whole exchange can sit inside a replayed CUDA graph.  The wait is bounded in TIME (%globaltimer,
+// GLIC_P2P_TIMEOUT_MS, default 20 s): a slow peer (first-iteration module load, graph instantiation, two ranks
+// time-sliced on one GPU) never trips it, a lost peer sets the sticky error word and lets the kernel end -- the context
+// stays healthy and the host reads the error with glic_p2p_check().
+__global__ void p2p_barrier_kernel(PeerBufs bufs, int rank, int world, size_t flag_off, unsigned long long timeout_ns) {
     const int q = threadIdx.x;
     uint32_t epoch = 0;
+    uint32_t* own = reinterpret_cast<uint32_t*>(bufs.p[rank] + flag_off);
     if (q == 0) {
-        uint32_t* ctr = reinterpret_cast<uint32_t*>(bufs.p[rank] + flag_off) + P2P_MAX_RANKS;
-        epoch = *ctr + 1;
-        *ctr = epoch;
+        epoch = own[P2P_EPOCH_WORD] + 1;
+        own[P2P_EPOCH_WORD] = epoch;
     }
     epoch = __shfl_sync(0xffffffffu, epoch, 0);
     if (q >= world) return;
     __threadfence_system();
     uint32_t* remote = reinterpret_cast<uint32_t*>(bufs.p[q] + flag_off) + rank;
     st_release_sys(remote, epoch);
-    const uint32_t* local = reinterpret_cast<const uint32_t*>(bufs.p[rank] + flag_off) + q;
-    unsigned long long spins = 0;
+    const uint32_t* local = own + q;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int polls = 0;
     while ((int)(ld_acquire_sys(local) - epoch) < 0) {
-        if (++spins > (1ull << 28)) __trap();       // a lost peer must not hang this GPU forever
+        if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+            own[P2P_ERROR_WORD] = 1u;
+            break;
+        }
     }
 }
 
@@ -97,6 +116,15 @@ p2p_reduce_kernel(PeerBufs bufs, size_t lo4, size_t hi4, size_t vis_off, size_t 
     }
 }
 
+unsigned long long p2p_timeout_ns() {
+    static const unsigned long long ns = [] {
+        const char* e = getenv("GLIC_P2P_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 20000;
+        return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+    }();
+    return ns;
+}
+
 template <int WORLD, int UNROLL>
 void launch_reduce(const PeerBufs& pb, size_t lo4, size_t hi4, size_t vis_off, size_t vlo4, size_t vhi4, int ctas_per_sm, cudaStream_t s) {
     const size_t work = std::max((hi4 - lo4 + UNROLL - 1) / UNROLL, vhi4 - vlo4);
@@ -140,11 +168,7 @@ p2p_reduce_adam_kernel(PeerBufs bufs, int rank, size_t lo4, size_t hi4, size_t v
 #pragma unroll
             for (int q = 0; q < 5; ++q) grp += j >= L.end[q];
             if (!visible[(j - L.begin[grp]) / L.k[grp]]) continue;
-            // adam_kernel's arithmetic (adamUpdateCUDA, adam.cu:9-38), element for element
-            const float mm = b1 * m[c] + (1.0f - b1) * g[c];
-            const float vv = b2 * v[c] + (1.0f - b2) * g[c] * g[c];
-            p[c] += -L.lr[grp] * mm / (sqrtf(vv) + eps);
-            m[c] = mm; v[c] = vv;
+            adam_element(p[c], m[c], v[c], g[c], L.lr[grp], b1, b2, eps);     // adam_math.cuh: shared with adam_kernel / adam_packed_kernel
         }
         exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
         exp_avg_sq[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -213,7 +237,7 @@ int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t 
     glic_p2p_slice(rank, world, n_floats, n_vis_bytes, sl);
     const size_t lo4 = sl[0], hi4 = sl[1], vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
     { StageTimer _t(GLIC_STAGE_ALLREDUCE, s);
-      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);         // every peer's gradients are complete
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off, p2p_timeout_ns());         // every peer's gradients are complete
       GLIC_LAUNCH_CHECK();
       static const int ctas = getenv("GLIC_P2P_CTAS") ? atoi(getenv("GLIC_P2P_CTAS")) : 2;   // tuning knobs, see profiles/
       static const int unr = getenv("GLIC_P2P_UNROLL") ? atoi(getenv("GLIC_P2P_UNROLL")) : 4;
@@ -225,8 +249,27 @@ int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t 
       }
 #undef GLIC_P2P_CASE
       GLIC_LAUNCH_CHECK();
-      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);      // every slice has been written everywhere
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off, p2p_timeout_ns());      // every slice has been written everywhere
       GLIC_LAUNCH_CHECK(); }
+    return GLIC_OK;
+}
+
+// Synchronises `stream` and reports a barrier timeout recorded by any earlier exchange on this rank's buffer
+// (GLIC_ERR_TIMEOUT; the error word is cleared).  buf = this rank's own block.
+int glic_p2p_check(void* buf, size_t n_floats, size_t n_vis_bytes, void* stream) {
+    if (!buf) { set_error("p2p_check: null buffer"); return GLIC_ERR_INVALID_ARGUMENT; }
+    size_t sl[6];
+    glic_p2p_slice(0, 1, n_floats, n_vis_bytes, sl);
+    uint32_t* word = reinterpret_cast<uint32_t*>(static_cast<char*>(buf) + sl[5]) + P2P_ERROR_WORD;
+    uint32_t err = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    GLIC_CUDA_TRY(cudaMemcpyAsync(&err, word, sizeof(err), cudaMemcpyDeviceToHost, s));
+    GLIC_CUDA_TRY(cudaStreamSynchronize(s));
+    if (err) {
+        GLIC_CUDA_TRY(cudaMemsetAsync(word, 0, sizeof(err), s));
+        set_error("p2p exchange: a peer did not reach the barrier within GLIC_P2P_TIMEOUT_MS");
+        return GLIC_ERR_TIMEOUT;
+    }
     return GLIC_OK;
 }
 
@@ -257,13 +300,13 @@ int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P
     const size_t lo4 = std::min(sl[0], used4), hi4 = std::min(sl[1], used4), vlo4 = sl[2], vhi4 = sl[3], f_bytes = sl[4], flag_off = sl[5];
     const size_t params_off = flag_off + 256;
     { StageTimer _t(GLIC_STAGE_ALLREDUCE, s);
-      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // every peer's gradients and visibility are complete
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off, p2p_timeout_ns());          // every peer's gradients and visibility are complete
       GLIC_LAUNCH_CHECK();
 #define GLIC_P2P_VIS(WD) case WD: launch_reduce<WD, 1>(pb, 0, 0, f_bytes, vlo4, vhi4, 2, s); break;
       switch (world) { GLIC_P2P_VIS(1) GLIC_P2P_VIS(2) GLIC_P2P_VIS(3) GLIC_P2P_VIS(4) GLIC_P2P_VIS(5) GLIC_P2P_VIS(6) GLIC_P2P_VIS(7) GLIC_P2P_VIS(8) }
 #undef GLIC_P2P_VIS
       GLIC_LAUNCH_CHECK();
-      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // the visibility union is everywhere
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off, p2p_timeout_ns());          // the visibility union is everywhere
       GLIC_LAUNCH_CHECK();
       const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((hi4 - lo4 + 255) / 256, (size_t)148 * 4));
 #define GLIC_P2P_ADAM(WD) case WD: p2p_reduce_adam_kernel<WD><<<blocks, 256, 0, s>>>(pb, rank, lo4, hi4, f_bytes, params_off, \
@@ -271,7 +314,7 @@ int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P
       switch (world) { GLIC_P2P_ADAM(1) GLIC_P2P_ADAM(2) GLIC_P2P_ADAM(3) GLIC_P2P_ADAM(4) GLIC_P2P_ADAM(5) GLIC_P2P_ADAM(6) GLIC_P2P_ADAM(7) GLIC_P2P_ADAM(8) }
 #undef GLIC_P2P_ADAM
       GLIC_LAUNCH_CHECK();
-      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off);          // every parameter slice has been written everywhere
+      p2p_barrier_kernel<<<1, 32, 0, s>>>(pb, rank, world, flag_off, p2p_timeout_ns());          // every parameter slice has been written everywhere
       GLIC_LAUNCH_CHECK(); }
     return GLIC_OK;
 }

@@ -104,13 +104,14 @@ def make_gt_image(W, H, seed=7):
     return img.astype(np.float32)
 
 
-def make_scene(name="cfg1", P=None, seed=42, view=0, **overrides):
+def make_scene(name="cfg1", P=None, seed=42, view=0, pp=(0.0, 0.0), radius=2.0, **overrides):
+    """Gaussians of config `name` + the camera of rig view `view`; pp = principal-point offset (pixels) from the config's."""
     Pn, W, H, fx, fy, cx, cy, deg, zmax = CONFIGS[name]
     P = Pn if P is None else P
     deg = overrides.pop("sh_degree", deg)
     g = make_gaussians(P, W, H, fx, fy, sh_degree=deg, zmax=zmax, seed=seed, **overrides)
-    R_wc, t_wc = orbit_pose(view)
-    cam = make_camera(W, H, fx, fy, cx, cy, R_wc, t_wc)
+    R_wc, t_wc = orbit_pose(view, radius=radius)
+    cam = make_camera(W, H, fx, fy, cx + pp[0], cy + pp[1], R_wc, t_wc)
     return g, cam
 
 

@@ -43,7 +43,8 @@ typedef enum glic_status {
     GLIC_ERR_INVALID_ARGUMENT = -1, /* bad shape / null pointer / unsupported degree        */
     GLIC_ERR_WORKSPACE = -2,        /* a workspace is smaller than glic_*_bytes() requires   */
     GLIC_ERR_CUDA = -3,             /* a CUDA runtime call failed (text in glic_last_error)  */
-    GLIC_ERR_NO_DEVICE = -4         /* no CUDA device / wrong architecture                   */
+    GLIC_ERR_NO_DEVICE = -4,        /* no CUDA device / wrong architecture                   */
+    GLIC_ERR_TIMEOUT = -5           /* a multi-GPU peer did not reach the exchange barrier   */
 } glic_status;
 
 /* Tile geometry is part of the parity contract (rasterizer/cuda_rasterizer/config.h:16-17). */
@@ -273,6 +274,10 @@ GLIC_API int glic_p2p_close(void* peer_ptr);
 GLIC_API int glic_p2p_free(void* dev_ptr);
 GLIC_API int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host, size_t n_floats, size_t n_vis_bytes,
                                      void* stream);
+/* The device-side barriers wait at most GLIC_P2P_TIMEOUT_MS (environment, default 20000) for a peer; a timeout sets a
+ * sticky error word in the rank's own block instead of hanging or trapping.  glic_p2p_check synchronises `stream` and
+ * returns GLIC_ERR_TIMEOUT if one was recorded since the last check (and clears it). */
+GLIC_API int glic_p2p_check(void* own_buf, size_t n_floats, size_t n_vis_bytes, void* stream);
 
 /* EXPERIMENTAL -- fused exchange + optimiser: reduce-scatter of the gradients, visibility-masked Adam on the local slice,
  * all-gather of the updated PARAMETERS, in one kernel over peer memory (same NVLink bytes as the all-reduce, Adam traffic

@@ -21,11 +21,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from gaussian_lic_b200 import synthetic as syn  # noqa: E402
 from helpers import small_scene  # noqa: E402
 
-SCENES = {  # name: (P, W, H, seed, degree) -- P multiple of 256 (reference tail-thread race)
-    "scene_deg3": (2048, 160, 112, 21, 3),
-    "scene_deg0": (1024, 96, 64, 22, 0),
-    "scene_deg1": (1536, 128, 80, 23, 1),
+SCENES = {  # name: (P, W, H, seed, degree, view, pp) -- P multiple of 256 (reference tail-thread race)
+    "scene_deg3": (2048, 160, 112, 21, 3, 0, (0.0, 0.0)),
+    "scene_deg0": (1024, 96, 64, 22, 0, 0, (0.0, 0.0)),
+    "scene_deg1": (1536, 128, 80, 23, 1, 0, (0.0, 0.0)),
+    # rotated + translated rig view with an off-centre principal point (R != I, t != 0, four distinct lim* clamps)
+    "scene_rot_deg3": (4096, 160, 112, 24, 3, 3, (7.5, -4.25)),
+    "scene_rot_deg2": (3072, 128, 80, 25, 2, 1, (-5.0, 3.5)),
 }
+ONLY = [a for a in sys.argv[2:]]          # optional: regenerate only these scenes (others keep their committed vectors)
 
 
 def load_ref():
@@ -40,8 +44,10 @@ def main(out_dir):
     os.makedirs(out_dir, exist_ok=True)
     ref = load_ref()
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
-    for name, (P, W, H, seed, deg) in SCENES.items():
-        g, cam = small_scene(P, W, H, seed, deg)
+    for name, (P, W, H, seed, deg, view, pp) in SCENES.items():
+        if ONLY and name not in ONLY:
+            continue
+        g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
         lims = [float(x) for x in cam["lims"]]
         a = dict(means=t(g["means"]), opac=t(g["opacity"]).view(P, 1), scales=t(g["scales"]), rots=t(g["rots"]),
                  dc=t(g["dc"]).view(P, 1, 3), sh=t(g["sh"]), view=t(cam["view"]).view(4, 4), proj=t(cam["proj"]).view(4, 4),
@@ -61,12 +67,14 @@ def main(out_dir):
         vis = (radii > 0).cpu().numpy()
         c = lambda x: x.detach().cpu().numpy()
         np.savez_compressed(
-            os.path.join(out_dir, name + ".npz"), P=P, W=W, H=H, seed=seed, degree=deg, R=R, B=B, color=c(color), final_T=c(final_T),
+            os.path.join(out_dir, name + ".npz"), P=P, W=W, H=H, seed=seed, degree=deg, view=view, pp=np.asarray(pp, np.float64), R=R, B=B, color=c(color), final_T=c(final_T),
             radii=c(radii), tiles_touched=c(tiles), depth_bits=c(depths).view(np.uint32) * vis, xy_bits=c(means2D).view(np.uint32) * vis[:, None],
             conic_opacity_bits=c(conic_o).view(np.uint32) * vis[:, None], point_list=c(plist), ranges=c(ranges),
             bucket_offsets=c(bucket_offsets), n_contrib=c(n_contrib), dL_dpix_seed=seed,
             **{n: c(x) for n, x in zip(names, grads)})
         print(name, "R", R, "B", B, "visible", int(vis.sum()))
+    if ONLY and "aux_ops" not in ONLY:
+        return
     # auxiliary operators
     gen = torch.Generator(device="cuda").manual_seed(5)
     img1 = torch.rand(1, 3, 72, 100, device="cuda", generator=gen)

@@ -7,8 +7,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GLIC_EXPERIMENTAL") != "1",
-                                                  reason="experimental kernels: set GLIC_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 

@@ -16,9 +16,9 @@ torch = pytest.importorskip("torch")
 COLOR_ATOL = 1e-4          # north_star tolerance for colour / transmittance
 
 
-def _run(cfg, P=None, view=0):
+def _run(cfg, P=None, view=0, pp=(0.0, 0.0)):
     from gaussian_lic_b200 import ops, synthetic as syn
-    g, cam = syn.make_scene(cfg, P=P, view=view)
+    g, cam = syn.make_scene(cfg, P=P, view=view, pp=pp)
     W, H = cam["W"], cam["H"]
     r = ops.CRasterizer(W, H)
     gd = ops.scene_to_device(g)
@@ -90,12 +90,14 @@ def test_backward_linearity_and_culled_zero_fullsize():
         grad_close((0.5 * b).cpu().numpy(), a.cpu().numpy(), k + " linearity", rtol=2e-4)
 
 
-def test_cfg2_matches_reference_build(ref_ext):
+@pytest.mark.parametrize("view,pp", [(0, (0.0, 0.0)), (1, (0.0, 0.0)), (3, (0.0, 0.0)), (5, (41.5, -27.25))])
+def test_cfg2_matches_reference_build(ref_ext, view, pp):
     """The BASELINE workload itself against the reference's CUDA build (P trimmed to a multiple of 256: the reference's
-    tail threads alias Gaussian P-1)."""
+    tail threads alias Gaussian P-1), from the identity pose, from rotated + translated rig views (what
+    ranks 1..7 of the multi-GPU runs render) and with an off-centre principal point."""
     from test_gpu_reference_pin import _ref_forward
     P = 499_968
-    g, cam, r, gd, v, color, T, radii = _run("cfg2", P)
+    g, cam, r, gd, v, color, T, radii = _run("cfg2", P, view=view, pp=pp)
     H, W = cam["H"], cam["W"]
     args, out = _ref_forward(ref_ext, g, cam)
     R, B, rcolor, rT, rradii, geomB, binB, imgB, smpB = out

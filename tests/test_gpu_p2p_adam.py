@@ -8,8 +8,7 @@ import socket
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GLIC_EXPERIMENTAL") != "1",
-                                                  reason="experimental kernels: set GLIC_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 P, M = 10007, 15
 LR6 = [1e-3, 1.6e-4, 5e-3, 5e-2, 2.5e-3, 1.25e-4]

@@ -6,7 +6,7 @@ Tolerance (1e-4 abs, see helpers.py): colour, transmittance; gradients relative 
 import numpy as np
 import pytest
 
-from helpers import grad_close, image_close, small_scene
+from helpers import POSES, grad_close, image_close, small_scene
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -22,9 +22,10 @@ def _run_cuda(g, cam, no_color=False):
     return r, gd, view, color, T, radii
 
 
+@pytest.mark.parametrize("view,pp", POSES)
 @pytest.mark.parametrize("P,W,H,deg,seed", [(3000, 320, 208, 3, 11), (10000, 640, 480, 0, 42), (20000, 500, 300, 2, 7)])
-def test_forward_matches_oracle(oracle32, P, W, H, deg, seed):
-    g, cam = small_scene(P, W, H, seed, deg)
+def test_forward_matches_oracle(oracle32, P, W, H, deg, seed, view, pp):
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     r, gd, view, color, T, radii = _run_cuda(g, cam)
     f = oracle32.forward(g, cam)
     st = oracle32.state(f)
@@ -59,9 +60,10 @@ def test_forward_no_color(oracle32):
     oracle32.free(f)
 
 
+@pytest.mark.parametrize("view,pp", POSES)
 @pytest.mark.parametrize("P,W,H,deg,seed", [(3000, 320, 208, 3, 11), (10000, 640, 480, 0, 42), (8000, 333, 211, 1, 5)])
-def test_backward_matches_oracle(oracle32, P, W, H, deg, seed):
-    g, cam = small_scene(P, W, H, seed, deg)
+def test_backward_matches_oracle(oracle32, P, W, H, deg, seed, view, pp):
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     r, gd, view, color, T, radii = _run_cuda(g, cam)
     rng = np.random.default_rng(seed)
     dL = rng.normal(size=(3, H, W)).astype(np.float32)

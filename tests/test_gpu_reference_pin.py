@@ -8,7 +8,7 @@ Skipped when oracle/_ref/glic_ref_ext.so has not been built (it is built in the 
 import numpy as np
 import pytest
 
-from helpers import grad_close, image_close, small_scene
+from helpers import POSES, grad_close, image_close, small_scene
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -30,10 +30,11 @@ def _ref_forward(ref, g, cam, no_color=False):
 
 
 # P is a multiple of 256 so the reference's tail-thread aliasing race cannot hit Gaussian P-1.
+@pytest.mark.parametrize("view,pp", POSES)
 @pytest.mark.parametrize("P,W,H,deg,seed", [(4096, 320, 208, 3, 11), (10240, 640, 480, 0, 42), (25600, 800, 450, 3, 8)])
-def test_cuda_path_vs_reference(ref_ext, P, W, H, deg, seed):
+def test_cuda_path_vs_reference(ref_ext, P, W, H, deg, seed, view, pp):
     from gaussian_lic_b200 import ops
-    g, cam = small_scene(P, W, H, seed, deg)
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     args, out = _ref_forward(ref_ext, g, cam)
     R, B, color, final_T, radii, geomB, binB, imgB, smpB = out
     r = ops.CRasterizer(W, H)
@@ -77,10 +78,11 @@ def test_cuda_path_vs_reference(ref_ext, P, W, H, deg, seed):
             grad_close(mine[n].cpu().numpy().reshape(rg.shape), rg.cpu().numpy(), n + " vs reference", rtol=5e-4)
 
 
+@pytest.mark.parametrize("view,pp", POSES)
 @pytest.mark.parametrize("P,W,H,deg,seed", [(4096, 320, 208, 3, 11), (10240, 640, 480, 0, 42)])
-def test_cpu_oracle_vs_reference(ref_ext, oracle32, P, W, H, deg, seed):
+def test_cpu_oracle_vs_reference(ref_ext, oracle32, P, W, H, deg, seed, view, pp):
     """Pins oracle/glic_oracle.c against outputs of the reference itself."""
-    g, cam = small_scene(P, W, H, seed, deg)
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     args, out = _ref_forward(ref_ext, g, cam)
     R, B, color, final_T, radii, geomB, binB, imgB, smpB = out
     f = oracle32.forward(g, cam)

@@ -17,11 +17,13 @@ def _load(name):
     return np.load(p)
 
 
-@pytest.mark.parametrize("name", ["scene_deg3", "scene_deg0", "scene_deg1"])
+@pytest.mark.parametrize("name", ["scene_deg3", "scene_deg0", "scene_deg1", "scene_rot_deg3", "scene_rot_deg2"])
 def test_oracle_matches_reference_golden(oracle32, name):
     z = _load(name)
     P, W, H, seed, deg = (int(z[k]) for k in ("P", "W", "H", "seed", "degree"))
-    g, cam = small_scene(P, W, H, seed, deg)
+    view = int(z["view"]) if "view" in z.files else 0
+    pp = tuple(float(x) for x in z["pp"]) if "pp" in z.files else (0.0, 0.0)
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     f = oracle32.forward(g, cam)
     st = oracle32.state(f)
     # integer contract: bit-exact
