@@ -35,6 +35,20 @@ METRIC = "Gaussians/sec rasterized (fwd+bwd) @1920x1080"
 LAMBDA_DSSIM = 0.2
 
 
+def load_synthetic():
+    """gaussian_lic_b200/synthetic.py (pure numpy) loaded BY PATH: importing the package would dlopen libglic_b200.so,
+    and the reference arm must not have the product library mapped at all."""
+    import importlib.util
+    name = "_glic_synthetic"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "gaussian_lic_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -125,8 +139,8 @@ def physical_cores():
 
 def cpu_baseline(cfg, sample_P, threads_note=True):
     """CPU oracle (port) timed on the host cores on a bounded sample: same recipe, fewer Gaussians."""
-    from gaussian_lic_b200 import synthetic as syn
     from oracle.oracle import Oracle
+    syn = load_synthetic()
     o = Oracle(np.float32)
     o.set_threads(physical_cores())                        # torchrun exports OMP_NUM_THREADS=1; use the host cores we have
     g, cam = syn.make_scene(cfg, P=sample_P)
@@ -164,6 +178,54 @@ def max_over_ranks(ms, world):
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_ranks(ms, world):
+    if world == 1:
+        return [ms]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
+def timed_windows(run_step, steps, world, dev, min_windows=5, min_total_ms=500.0, max_windows=60):
+    """Device-timed windows of EXACTLY `steps` steps each.  Every window is bracketed by a barrier +
+    torch.cuda.synchronize() on both sides and timed with a CUDA event pair on the launching stream; a window's time is
+    the MAX over ranks.  The reported figure is the MEDIAN window (>= 5 windows and >= 0.5 s of timed work in total),
+    so one host-side hiccup on one rank (a 100 ms stall inside a 30 ms window was the round-1 N = 8 collapse) cannot
+    set the number; every window is returned so the spread is visible.  -> (median ms/step, [window ms/step], per-rank
+    ms/step of the median window)."""
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wins, ranks = [], []
+    n = min_windows
+    i = 0
+    while i < n:
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            run_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        mine = e0.elapsed_time(e1) / steps
+        wins.append(max_over_ranks(mine, world))
+        ranks.append(mine)
+        if i == 0:                                           # identical on every rank (max-reduced): same window count
+            n = int(min(max_windows, max(min_windows, -(-min_total_ms // max(wins[0] * steps, 1e-3)))))
+        i += 1
+    order = sorted(range(len(wins)), key=lambda k: wins[k])
+    mid = order[len(order) // 2]
+    return wins[mid], [round(w, 4) for w in wins], [round(x, 4) for x in gather_ranks(ranks[mid], world)]
 
 
 def run_ours(args):
@@ -248,29 +310,23 @@ def run_ours(args):
             graph, r.stream = None, None
             torch.cuda.synchronize(dev)
     run_step = graph.replay if graph is not None else step
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
+    # clock sampler first (its process start must not land between the barrier and the first event), then the windows
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)
     l0 = capi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    e0.record()
-    for _ in range(args.steps):
-        run_step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    ms_step, windows, per_rank = timed_windows(run_step, args.steps, world, dev)
     launches = capi.launch_count() - l0
     if graph is not None:                                  # replays do not pass through the launch counter
+        l0 = capi.launch_count()
         step(); torch.cuda.synchronize(dev)
         launches = (capi.launch_count() - l0) * args.steps
+    else:
+        launches //= len(windows)
     assert not r.finish(), "binning capacity overflow inside the timed region"
     clocks = sampler.stop() if rank == 0 else None
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     value = P * world / (ms_step * 1e-3)
 
     # ---- per-stage timing for the roofline (separate pass; events on the launching stream) ---------------
@@ -471,6 +527,8 @@ def run_ours(args):
     cpu, _ = cpu_baseline(cfg, min(P, args.cpu_sample))
     out = {"metric": METRIC, "value": value, "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+           "timing": {"how": "median of %d device-timed windows of exactly %d steps (barrier + sync both sides, max over ranks per window)"
+                             % (len(windows), args.steps), "window_ms_per_step": windows, "per_rank_ms_per_step": per_rank},
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s: %d Gaussians, %dx%d, SH degree %d, forward + fused L1/D-SSIM loss + backward, "
                                   "1 view per GPU" % (cfg, P, W, H, deg),
@@ -489,7 +547,7 @@ def run_reference(args):
     if rank != 0:
         return
     import importlib.util
-    from gaussian_lic_b200 import synthetic as syn
+    syn = load_synthetic()
     cfg = args.config
     P, W, H, fx, fy, cx, cy, deg, zmax = syn.CONFIGS[cfg]
     so = os.path.join(ROOT, "oracle", "_ref", "glic_ref_ext.so")

@@ -216,9 +216,9 @@ using namespace glic;
 
 extern "C" int glic_adam_update(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* visible,
                                 float lr, float b1, float b2, float eps, uint32_t N, uint32_t M, void* stream) {
-    if (!param || !grad || !exp_avg || !exp_avg_sq || !visible) { set_error("adam: null pointer"); return GLIC_ERR_INVALID_ARGUMENT; }
     const size_t total = (size_t)N * M;
-    if (total == 0) return GLIC_OK;
+    if (total == 0) return GLIC_OK;       // an empty group (sh-rest at degree 0: [P,0,3]) has null data pointers; the reference launches nothing
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !visible) { set_error("adam: null pointer"); return GLIC_ERR_INVALID_ARGUMENT; }
     const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148u * 32u);
     StageTimer _t(GLIC_STAGE_ADAM, (cudaStream_t)stream);
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps, N, M);

@@ -320,6 +320,42 @@ int glic_backward(int P, int sh_degree, int M, const float* means3D, const float
                                       dL_dsh, dL_dscales, dL_drotations, s);
 }
 
+// Internal (mapper.cu): the backward with the compact gradient form of preprocess_backward.cu.  dL_dcolors is zeroed and
+// accumulated like the other 2-D gradients but may live anywhere (the mapper points it into its exchange block).
+int glic_backward_compact_internal(int P, int sh_degree, int M, const float* means3D, const float* scales, const float* rotations,
+                                   const float* sh, const glic_view* view, const int* radii, int64_t R, const void* geom_ws,
+                                   const void* binning_ws, const void* image_ws, const void* sample_ws, const float* dL_dpix,
+                                   float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
+                                   const glic::CompactGrads* cg, void* after_render_event, void* stream) {
+    if (int e = check_view(view)) return e;
+    if (P <= 0) return GLIC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const ViewParams vp = make_view_params(view);
+    GeomState g = GeomState::carve(const_cast<void*>(geom_ws), P);
+    ImageState img = ImageState::carve(const_cast<void*>(image_ws), vp.W, vp.H);
+    { StageTimer _t(GLIC_STAGE_ZERO, s);
+    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 4 * (size_t)P, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)P, s));
+    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, s)); }
+    if (R > 0) {
+        BinningState bin = BinningState::carve(const_cast<void*>(binning_ws), R);
+        const int64_t max_buckets = glic_max_buckets(R, vp.W, vp.H);
+        SampleState smp = SampleState::carve(const_cast<void*>(sample_ws), max_buckets);
+        const int T = vp.grid_x * vp.grid_y;
+        const int passes = ((int)higher_msb((uint32_t)T) + 7) / 8;
+        const int cur = passes & 1;
+        StageTimer _t(GLIC_STAGE_RENDER_BWD, s);
+        if (int e = launch_render_backward(P, vp, max_buckets, bin.vals[cur], g, img, smp, dL_dpix, dL_dmeans2D, dL_dconic,
+                                           dL_dopacity, dL_dcolors, s)) return e;
+    }
+    // the colour gradients are final here: the multi-GPU push may start while the per-Gaussian backward still runs
+    if (after_render_event) GLIC_CUDA_TRY(cudaEventRecord((cudaEvent_t)after_render_event, s));
+    StageTimer _t(GLIC_STAGE_PREPROCESS_BWD, s);
+    return launch_preprocess_backward_compact(P, sh_degree, M, means3D, scales, 1.0f, rotations, sh, vp, radii, g, dL_dmeans2D,
+                                              dL_dconic, dL_dcolors, *cg, s);
+}
+
 int glic_sort_pairs_u64_u32(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out,
                             uint32_t* vals_out, void* temp, size_t temp_bytes, void* stream) {
     if (n < 0 || (n > 0 && (!keys_in || !vals_in || !keys_out || !vals_out || !temp))) { set_error("sort_pairs: bad arguments"); return GLIC_ERR_INVALID_ARGUMENT; }

@@ -235,6 +235,18 @@ inline ViewParams make_view_params(const glic_view* v) {
     return p;
 }
 
+// Compact gradient outputs of the per-Gaussian backward (the mapper's form, see preprocess_backward.cu).
+struct CompactGrads {
+    float4* g_rot;            // [P] dL/d(raw rotation)
+    float* g_xyz;             // [P,3]
+    float* g_scale;           // [P,3] dL/d(log-scale)
+    float* g_opacity;         // [P]   dL/d(opacity logit)
+    const float* opacity;     // [P]   activated opacity (sigmoid output)
+    const float* dL_dopacity; // [P]   dL/d(activated opacity) from the render backward
+    const float4* rot_raw;    // [P]   raw (un-normalised) rotation
+    int accumulate;           // 0: overwrite the geometric gradients, 1: add to them (second and later views of a rank)
+};
+
 // ---- stage launchers (defined in the .cu files) ------------------------------------------
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
                               const float* rots, const float* opac, const float* dc, const float* sh,
@@ -261,4 +273,24 @@ int launch_preprocess_backward(int P, int D, int M, const float* means, const fl
                                const float* dL_dcolors, float* dL_dmeans3D, float* dL_dcov3D, float* dL_ddc,
                                float* dL_dsh, float* dL_dscales, float* dL_drots, cudaStream_t s);
 
+int launch_preprocess_backward_compact(int P, int D, int M, const float* means, const float* scales, float mod,
+                                       const float* rots, const float* sh, const ViewParams& vp, const int* radii, GeomState g,
+                                       const float* dL_dmean2D, const float* dL_dconic, const float* dL_dcolors,
+                                       const CompactGrads& cg, cudaStream_t s);
+
+}  // namespace glic
+
+// internal cross-file entry points (not part of the C ABI)
+extern "C" int glic_backward_compact_internal(int P, int sh_degree, int M, const float* means3D, const float* scales,
+                                              const float* rotations, const float* sh, const glic_view* view, const int* radii,
+                                              int64_t R, const void* geom_ws, const void* binning_ws, const void* image_ws,
+                                              const void* sample_ws, const float* dL_dpix, float* dL_dmeans2D, float* dL_dconic,
+                                              float* dL_dopacity, float* dL_dcolors, const glic::CompactGrads* cg,
+                                              void* after_render_event, void* stream);
+namespace glic {
+int launch_adam_compact(uint32_t P, uint32_t Pcap, int D, int M, float* params, float* exp_avg, float* exp_avg_sq, const float* g_geo,
+                        uint32_t Pcap_geo, const float* lr6, const float* g_color, const uint8_t* flags, const float* campos4,
+                        int n_slots, float grad_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
+                        unsigned int* visible_count, cudaStream_t s);
+int launch_view_flags(int P, const int* radii, const GeomState& g, uint8_t* flags, cudaStream_t s);
 }  // namespace glic

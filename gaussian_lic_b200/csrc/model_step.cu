@@ -10,6 +10,8 @@
 // that consumes that buffer (and, multi-GPU, exactly the bytes the exchange step just reduced).
 #include "common.cuh"
 #include "adam_math.cuh"
+#include "sh_math.cuh"
+#include "warp_rows.cuh"
 #include <algorithm>
 
 namespace glic {
@@ -83,6 +85,137 @@ adam_packed_kernel(float* __restrict__ param, const float* __restrict__ grad, fl
     }
 }
 
+
+// ---- the mapper's Adam: compact gradients in, all six groups out (include/glic_b200.h "Native mapping host") -----------
+// One warp owns 32 consecutive Gaussians.  Phase 1 (lane = Gaussian): the union of the per-view visibility bytes decides
+// whether the Gaussian steps at all; the 11 geometric gradients (already summed over the rank's views and mean-reduced over
+// the ranks) and dc take their Adam update straight from registers; the sh-rest gradient -- never materialised by the
+// backward -- is rebuilt as  sum_views b_k(dir_view) * g_view  (b_k: sh_math.cuh, dir from the PRE-update xyz) into a
+// shared-memory slab.  Phase 2 (warp-cooperative, coalesced): the 32 x 3M sh-rest parameters and moments stream through
+// once, reading their gradient from the slab.  Element arithmetic = adam_element (adam_math.cuh), i.e. adamUpdateCUDA's.
+struct ArenaLayout {
+    size_t off[6];       // float offset of each group in the arena: rotation, xyz, log-scale, opacity, dc, sh-rest
+    float lr[6];
+};
+
+struct ViewSlots {
+    const float* g_color;    // [n_slots][stride][3] dL/dcolour per view as the render backward left it (before the clamp mask)
+    const uint8_t* visible;  // [n_slots][stride] per-view flags: 0x80 = radii > 0, bits 0..2 = colour channel clamped (forward.cu:70-75)
+    const float* campos;     // [n_slots][4]
+    size_t stride;           // Gaussians per slot (the arena capacity)
+    int n_slots;
+};
+
+constexpr int ADAM_WARPS = 4;
+
+__global__ void __launch_bounds__(ADAM_WARPS * 32)
+adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                    const float* __restrict__ g_geo /* arena-shaped: rotation | xyz | log-scale | opacity */, ArenaLayout L,
+                    ArenaLayout Lg, ViewSlots vs, float grad_scale, float b1, float b2, float eps,
+                    const unsigned int* __restrict__ skip_flag, unsigned int* __restrict__ visible_count) {
+    __shared__ float s_g[ADAM_WARPS][32 * SH_ROW_MAX];
+    __shared__ uint8_t s_vis[ADAM_WARPS][32];
+    if (skip_flag && *skip_flag) return;                          // binning overflow: the frame was empty, do not step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wfirst = (blockIdx.x * ADAM_WARPS + warp) * 32u;
+    if (wfirst >= P) return;
+    const uint32_t i = wfirst + lane;
+    const int K = 3 * M;
+    float* slab = s_g[warp];
+    bool vis = false;
+    if (i < P) {
+        for (int v = 0; v < vs.n_slots; ++v) vis |= (vs.visible[(size_t)v * vs.stride + i] & 0x80u) != 0;
+    }
+    s_vis[warp][lane] = vis ? 1 : 0;
+    const unsigned any = __ballot_sync(0xffffffffu, vis);
+    if (visible_count && lane == 0 && any) atomicAdd(visible_count, (unsigned)__popc(any));
+    if (!any) return;
+    if (vis) {
+        // ---- sh-rest gradient into the slab, dc gradient into registers (uses the pre-update position) ----
+        const float px = params[L.off[1] + 3 * (size_t)i], py = params[L.off[1] + 3 * (size_t)i + 1], pz = params[L.off[1] + 3 * (size_t)i + 2];
+        float gdc[3] = {0.f, 0.f, 0.f};
+        const int nb = D > 0 ? sh_rest_count(D) : 0;
+        float acc[SH_ROW_MAX];
+#pragma unroll
+        for (int k = 0; k < SH_ROW_MAX; ++k) acc[k] = 0.f;
+        for (int v = 0; v < vs.n_slots; ++v) {
+            const unsigned fl = vs.visible[(size_t)v * vs.stride + i];
+            if (!(fl & 0x80u)) continue;
+            const float* gc = vs.g_color + ((size_t)v * vs.stride + i) * 3;
+            const float g0 = (fl & 1u) ? 0.f : gc[0], g1 = (fl & 2u) ? 0.f : gc[1], g2 = (fl & 4u) ? 0.f : gc[2];
+            gdc[0] += kSH0 * g0; gdc[1] += kSH0 * g1; gdc[2] += kSH0 * g2;
+            if (nb > 0) {
+                const float ox = px - vs.campos[4 * v], oy = py - vs.campos[4 * v + 1], oz = pz - vs.campos[4 * v + 2];
+                const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+                float bs[15];
+                sh_basis(D, ox * inv, oy * inv, oz * inv, bs);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) {
+                    if (k < nb) { acc[3 * k] += bs[k] * g0; acc[3 * k + 1] += bs[k] * g1; acc[3 * k + 2] += bs[k] * g2; }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SH_ROW_MAX; ++k) if (k < K) slab[lane * K + k] = acc[k] * grad_scale;
+        // ---- geometric groups + dc: 14 scalars per Gaussian ----
+        auto step = [&](int grp, int kk, size_t j, float g) {
+            const size_t e = L.off[grp] + j;
+            float p = params[e], m = exp_avg[e], vv = exp_avg_sq[e];
+            adam_element(p, m, vv, g, L.lr[grp], b1, b2, eps);
+            params[e] = p; exp_avg[e] = m; exp_avg_sq[e] = vv;
+            (void)kk;
+        };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) step(0, 4, 4 * (size_t)i + c, g_geo[Lg.off[0] + 4 * (size_t)i + c] * grad_scale);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) step(1, 3, 3 * (size_t)i + c, g_geo[Lg.off[1] + 3 * (size_t)i + c] * grad_scale);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) step(2, 3, 3 * (size_t)i + c, g_geo[Lg.off[2] + 3 * (size_t)i + c] * grad_scale);
+        step(3, 1, (size_t)i, g_geo[Lg.off[3] + (size_t)i] * grad_scale);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) step(4, 3, 3 * (size_t)i + c, gdc[c] * grad_scale);
+    }
+    if (K == 0) return;
+    __syncwarp();
+    // ---- sh-rest: 32 rows of K floats, contiguous in the arena; rows of invisible Gaussians are skipped ----
+    const int cnt = (int)min(32u, P - wfirst);
+    const size_t base = L.off[5] + (size_t)wfirst * K;
+    for (int e = lane; e < cnt * K; e += 32) {
+        const int row = e / K;
+        if (!s_vis[warp][row]) continue;
+        float p = params[base + e], m = exp_avg[base + e], vv = exp_avg_sq[base + e];
+        adam_element(p, m, vv, slab[e], L.lr[5], b1, b2, eps);
+        params[base + e] = p; exp_avg[base + e] = m; exp_avg_sq[base + e] = vv;
+    }
+}
+
+// rows [P, P+n) of the arena <- the new Gaussians; their sh-rest rows and Adam moments are zero (densificationPostfix)
+__global__ void __launch_bounds__(256)
+arena_append_kernel(uint32_t P, uint32_t n, int K, ArenaLayout L, float* __restrict__ params, float* __restrict__ exp_avg,
+                    float* __restrict__ exp_avg_sq, const float* __restrict__ xyz, const float* __restrict__ f_dc,
+                    const float* __restrict__ log_scale, const float4* __restrict__ rot, const float* __restrict__ opacity_logit) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t i = (size_t)P + t;
+    reinterpret_cast<float4*>(params + L.off[0])[i] = rot[t];
+    reinterpret_cast<float4*>(exp_avg + L.off[0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(exp_avg_sq + L.off[0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        params[L.off[1] + 3 * i + c] = xyz[3 * (size_t)t + c];
+        params[L.off[2] + 3 * i + c] = log_scale[3 * (size_t)t + c];
+        params[L.off[4] + 3 * i + c] = f_dc[3 * (size_t)t + c];
+        exp_avg[L.off[1] + 3 * i + c] = 0.f; exp_avg_sq[L.off[1] + 3 * i + c] = 0.f;
+        exp_avg[L.off[2] + 3 * i + c] = 0.f; exp_avg_sq[L.off[2] + 3 * i + c] = 0.f;
+        exp_avg[L.off[4] + 3 * i + c] = 0.f; exp_avg_sq[L.off[4] + 3 * i + c] = 0.f;
+    }
+    params[L.off[3] + i] = opacity_logit[t];
+    exp_avg[L.off[3] + i] = 0.f; exp_avg_sq[L.off[3] + i] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        params[L.off[5] + i * K + k] = 0.f; exp_avg[L.off[5] + i * K + k] = 0.f; exp_avg_sq[L.off[5] + i * K + k] = 0.f;
+    }
+}
+
 }  // namespace
 }  // namespace glic
 
@@ -146,4 +279,76 @@ int glic_adam_update_packed(float* params, const float* grads, float* exp_avg, f
     return GLIC_OK;
 }
 
+int glic_arena_append(float* params, float* exp_avg, float* exp_avg_sq, uint32_t P, uint32_t Pcap, uint32_t M, uint32_t n_new,
+                      const float* xyz, const float* f_dc, const float* log_scale, const float* rot, const float* opacity_logit,
+                      void* stream) {
+    if (n_new == 0) return GLIC_OK;
+    if (!params || !exp_avg || !exp_avg_sq || !xyz || !f_dc || !log_scale || !rot || !opacity_logit) { set_error("arena_append: null pointer"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if ((Pcap & 3u) != 0 || !aligned16(params) || !aligned16(exp_avg) || !aligned16(exp_avg_sq) || !aligned16(rot)) {
+        set_error("arena_append: capacity must be a multiple of 4 and the buffers 16-byte aligned"); return GLIC_ERR_INVALID_ARGUMENT;
+    }
+    if ((uint64_t)P + n_new > Pcap) { set_error("arena_append: capacity exceeded (grow the arena with glic_arena_regrow first)"); return GLIC_ERR_WORKSPACE; }
+    ArenaLayout L;
+    size_t off6[6];
+    glic_packed_offsets(Pcap, M, off6);
+    for (int q = 0; q < 6; ++q) { L.off[q] = off6[q]; L.lr[q] = 0.f; }
+    arena_append_kernel<<<(n_new + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, n_new, (int)(3 * M), L, params, exp_avg, exp_avg_sq, xyz, f_dc,
+                                                                              log_scale, reinterpret_cast<const float4*>(rot), opacity_logit);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+int glic_arena_regrow(const float* src, uint32_t Pcap_src, float* dst, uint32_t Pcap_dst, uint32_t M, uint32_t P, void* stream) {
+    if (!src || !dst || P > Pcap_src || P > Pcap_dst) { set_error("arena_regrow: bad arguments"); return GLIC_ERR_INVALID_ARGUMENT; }
+    size_t a[6], b[6];
+    glic_packed_offsets(Pcap_src, M, a);
+    glic_packed_offsets(Pcap_dst, M, b);
+    const uint32_t k[6] = {4, 3, 3, 1, 3, 3 * M};
+    for (int q = 0; q < 6; ++q) {
+        if (!k[q] || !P) continue;
+        GLIC_CUDA_TRY(cudaMemcpyAsync(dst + b[q], src + a[q], sizeof(float) * (size_t)P * k[q], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return GLIC_OK;
+}
+
 }  // extern "C"
+
+// ---- launcher used by the mapper (mapper.cu) ---------------------------------------------------------------------
+namespace glic {
+namespace {
+__global__ void __launch_bounds__(256)
+view_flags_kernel(int P, const int* __restrict__ radii, const uint8_t* __restrict__ clamped, uint8_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) flags[i] = radii[i] > 0 ? (uint8_t)(0x80u | (clamped[i] & 7u)) : (uint8_t)0;
+}
+}  // namespace
+
+// per-view flags byte of the compact exchange: visibility + the forward's colour-clamp bits
+int launch_view_flags(int P, const int* radii, const GeomState& g, uint8_t* flags, cudaStream_t s) {
+    if (P <= 0) return GLIC_OK;
+    view_flags_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, radii, g.clamped, flags);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+int launch_adam_compact(uint32_t P, uint32_t Pcap, int D, int M, float* params, float* exp_avg, float* exp_avg_sq, const float* g_geo,
+                        uint32_t Pcap_geo, const float* lr6, const float* g_color, const uint8_t* flags, const float* campos4,
+                        int n_slots, float grad_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
+                        unsigned int* visible_count, cudaStream_t s) {
+    if (P == 0) return GLIC_OK;
+    ArenaLayout L, Lg;
+    size_t off6[6];
+    glic_packed_offsets(Pcap, (uint32_t)M, off6);
+    for (int q = 0; q < 6; ++q) { L.off[q] = off6[q]; L.lr[q] = lr6[q]; }
+    glic_packed_offsets(Pcap_geo, 0, off6);                         // geometric arena: rotation | xyz | log-scale | opacity
+    for (int q = 0; q < 6; ++q) { Lg.off[q] = off6[q]; Lg.lr[q] = 0.f; }
+    ViewSlots vs;
+    vs.g_color = g_color; vs.visible = flags; vs.campos = campos4; vs.stride = Pcap_geo; vs.n_slots = n_slots;
+    const unsigned warps = (P + 31) / 32;
+    StageTimer _t(GLIC_STAGE_ADAM, s);
+    adam_compact_kernel<<<(warps + ADAM_WARPS - 1) / ADAM_WARPS, ADAM_WARPS * 32, 0, s>>>(P, D, M, params, exp_avg, exp_avg_sq, g_geo, L, Lg, vs,
+                                                                                          grad_scale, b1, b2, eps, skip_flag, visible_count);
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+}  // namespace glic

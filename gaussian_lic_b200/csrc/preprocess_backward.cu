@@ -6,21 +6,23 @@
 // rasterize_points.cu:192-201: every output row is written here (exact zeros for culled
 // Gaussians).  Forward intermediates (cov3D, T) are recomputed from scale/rotation instead of
 // being stored (24 B/Gaussian less state, and the inputs are read anyway).
+//
+// Two output forms (template COMPACT):
+//   false: the reference's nine gradient tensors w.r.t. the ACTIVATED inputs (RasterizeGaussiansBackwardCUDA's contract);
+//   true : the mapper's compact form (include/glic_b200.h "Native mapping host"): 11 geometric floats per Gaussian
+//          w.r.t. the RAW parameters -- the sigmoid / exp / normalize chain rule (gaussian.cpp:147-175) applied here, with the
+//          expressions of activations_backward_kernel -- written or ACCUMULATED over a rank's views.  dL/d(dc, sh-rest) are
+//          not materialised: they are linear in the clamp-masked dL/dcolour (the render backward's output + the forward's
+//          clamp bits) and are rebuilt inside the Adam kernel (model_step.cu).
 #include "geom_math.cuh"
+#include "sh_math.cuh"
 #include "warp_rows.cuh"
 
 namespace glic {
 
-__device__ __constant__ float bSH_C1 = 0.4886025119029199f;
-__device__ __constant__ float bSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                                           -1.0925484305920792f, 0.5462742152960396f};
-__device__ __constant__ float bSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
-                                           0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
-                                           -0.5900435899266435f};
-constexpr float bSH_C0 = 0.28209479177387814f;
-
 constexpr int PB_THREADS = 128;
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(PB_THREADS)
 preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means, const float* __restrict__ scales,
                            float mod, const float4* __restrict__ rots, const float* __restrict__ sh, ViewParams vp,
@@ -28,7 +30,7 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
                            const float* __restrict__ dL_dmean2D, const float* __restrict__ dL_dconic,
                            const float* __restrict__ dL_dcolors, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dcov3D, float* __restrict__ dL_ddc, float* __restrict__ dL_dsh,
-                           float* __restrict__ dL_dscales, float4* __restrict__ dL_drots) {
+                           float* __restrict__ dL_dscales, float4* __restrict__ dL_drots, CompactGrads cg) {
     __shared__ float s_view[16], s_proj[16], s_cam[3];
     __shared__ __align__(16) float s_sh[PB_THREADS / 32][32 * SH_ROW_MAX];    // SH rows in, dL/dSH rows out
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -49,13 +51,22 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
     const bool visible = idx < P && radii[idx] > 0;
     if (!visible) {
         if (idx < P) {
+            if (COMPACT) {
+                if (!cg.accumulate) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { dL_dmeans3D[3 * idx + k] = 0.f; dL_ddc[3 * idx + k] = 0.f; dL_dscales[3 * idx + k] = 0.f; }
+                    for (int k = 0; k < 3; ++k) { cg.g_xyz[3 * idx + k] = 0.f; cg.g_scale[3 * idx + k] = 0.f; }
+                    cg.g_rot[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cg.g_opacity[idx] = 0.f;
+                }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = 0.f;
-            dL_drots[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 3; ++k) { dL_dmeans3D[3 * idx + k] = 0.f; dL_ddc[3 * idx + k] = 0.f; dL_dscales[3 * idx + k] = 0.f; }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = 0.f;
+                dL_drots[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        if (idx < P || staged) for (int k = 0; k < K; ++k) dsh[k] = 0.f;
+        if (!COMPACT && (idx < P || staged)) for (int k = 0; k < K; ++k) dsh[k] = 0.f;
     } else {
     const float px = means[3 * idx], py = means[3 * idx + 1], pz = means[3 * idx + 2];
     const float s0 = scales[3 * idx], s1 = scales[3 * idx + 1], s2 = scales[3 * idx + 2];
@@ -89,8 +100,10 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
         dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
         dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
     }
+    if (!COMPACT) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+    }
     const float* V = c3.c;
     // rows of T^T Vrk products: r0k = sum_m T0m * Vrk[k][m], r1k = sum_m T1m * Vrk[k][m]
     const float r00 = T00 * V[0] + T01 * V[1] + T02 * V[2], r10 = T10 * V[0] + T11 * V[1] + T12 * V[2];
@@ -122,21 +135,24 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
         dmz += (pr[8] * m_w - pr[11] * mul1) * g2x + (pr[9] * m_w - pr[11] * mul2) * g2y;
     }
 
-    // ---- SH backward (backward.cu:27-136).  Like the reference (`if (shs)`, backward.cu:352) the whole colour
-    // backward -- dL/ddc included -- is skipped when no SH-rest tensor is bound (M == 0). -------------------------
+    // ---- SH backward (computeColorFromSH's adjoint, backward.cu:27-136; factored as in sh_math.cuh).  Like the
+    // reference (`if (shs)`, backward.cu:352) the whole colour backward -- dL/ddc included -- is skipped when no SH-rest
+    // tensor is bound (M == 0). ----------------------------------------------------------------------------------
+    float dRGB[3] = {0.f, 0.f, 0.f};
     if (sh == nullptr) {
-        dL_ddc[3 * idx] = 0.f; dL_ddc[3 * idx + 1] = 0.f; dL_ddc[3 * idx + 2] = 0.f;
+        if (!COMPACT) { dL_ddc[3 * idx] = 0.f; dL_ddc[3 * idx + 1] = 0.f; dL_ddc[3 * idx + 2] = 0.f; }
     } else {
         const float ox = px - s_cam[0], oy = py - s_cam[1], oz = pz - s_cam[2];
         const float sum2 = ox * ox + oy * oy + oz * oz;
         const float inv = 1.0f / sqrtf(sum2);
         const float x = ox * inv, y = oy * inv, z = oz * inv;
         const unsigned cb = clamped[idx];
-        float dRGB[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) dRGB[ch] = (cb >> ch) & 1u ? 0.f : dL_dcolors[3 * idx + ch];
+        if (!COMPACT) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) dL_ddc[3 * idx + ch] = bSH_C0 * dRGB[ch];
+            for (int ch = 0; ch < 3; ++ch) dL_ddc[3 * idx + ch] = kSH0 * dRGB[ch];
+        }
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/d(dir)
         if (D > 0) {
             float sv[SH_ROW_MAX];                                  // input row -> registers (the slab row is reused for the output)
@@ -147,73 +163,39 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
 #pragma unroll
                 for (int k = 0; k < SH_ROW_MAX; ++k) sv[k] = k < K ? sh[(size_t)idx * K + k] : 0.f;
             }
-            const float* s = sv;   // rows are lane-private: no cross-lane hazard between this read and the dsh writes
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            float bs[15];
-            bs[0] = -bSH_C1 * y; bs[1] = bSH_C1 * z; bs[2] = -bSH_C1 * x;
-            int nb = 3;
-            if (D > 1) {
-                bs[3] = bSH_C2[0] * xy; bs[4] = bSH_C2[1] * yz; bs[5] = bSH_C2[2] * (2.f * zz - xx - yy);
-                bs[6] = bSH_C2[3] * xz; bs[7] = bSH_C2[4] * (xx - yy);
-                nb = 8;
-                if (D > 2) {
-                    bs[8] = bSH_C3[0] * y * (3.f * xx - yy);
-                    bs[9] = bSH_C3[1] * xy * z;
-                    bs[10] = bSH_C3[2] * y * (4.f * zz - xx - yy);
-                    bs[11] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                    bs[12] = bSH_C3[4] * x * (4.f * zz - xx - yy);
-                    bs[13] = bSH_C3[5] * z * (xx - yy);
-                    bs[14] = bSH_C3[6] * x * (xx - 3.f * yy);
-                    nb = 15;
-                }
-            }
+            const int nb = sh_rest_count(D);
+            float bs[15], w[15];
+            sh_basis(D, x, y, z, bs);
 #pragma unroll
             for (int k = 0; k < 15; ++k) {
                 if (k < nb) {
-                    dsh[3 * k + 0] = bs[k] * dRGB[0];
-                    dsh[3 * k + 1] = bs[k] * dRGB[1];
-                    dsh[3 * k + 2] = bs[k] * dRGB[2];
-                }
-            }
-            for (int k = nb; k < M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-#define SHc(k) s[(k) * 3 + ch]
-                float dx_ = -bSH_C1 * SHc(2), dy_ = -bSH_C1 * SHc(0), dz_ = bSH_C1 * SHc(1);
-                if (D > 1) {
-                    dx_ += bSH_C2[0] * y * SHc(3) + bSH_C2[2] * 2.f * -x * SHc(5) + bSH_C2[3] * z * SHc(6) + bSH_C2[4] * 2.f * x * SHc(7);
-                    dy_ += bSH_C2[0] * x * SHc(3) + bSH_C2[1] * z * SHc(4) + bSH_C2[2] * 2.f * -y * SHc(5) + bSH_C2[4] * 2.f * -y * SHc(7);
-                    dz_ += bSH_C2[1] * y * SHc(4) + bSH_C2[2] * 2.f * 2.f * z * SHc(5) + bSH_C2[3] * x * SHc(6);
-                    if (D > 2) {
-                        dx_ += bSH_C3[0] * SHc(8) * 3.f * 2.f * xy + bSH_C3[1] * SHc(9) * yz + bSH_C3[2] * SHc(10) * -2.f * xy +
-                               bSH_C3[3] * SHc(11) * -3.f * 2.f * xz + bSH_C3[4] * SHc(12) * (-3.f * xx + 4.f * zz - yy) +
-                               bSH_C3[5] * SHc(13) * 2.f * xz + bSH_C3[6] * SHc(14) * 3.f * (xx - yy);
-                        dy_ += bSH_C3[0] * SHc(8) * 3.f * (xx - yy) + bSH_C3[1] * SHc(9) * xz +
-                               bSH_C3[2] * SHc(10) * (-3.f * yy + 4.f * zz - xx) + bSH_C3[3] * SHc(11) * -3.f * 2.f * yz +
-                               bSH_C3[4] * SHc(12) * -2.f * xy + bSH_C3[5] * SHc(13) * -2.f * yz + bSH_C3[6] * SHc(14) * -3.f * 2.f * xy;
-                        dz_ += bSH_C3[1] * SHc(9) * xy + bSH_C3[2] * SHc(10) * 4.f * 2.f * yz +
-                               bSH_C3[3] * SHc(11) * 3.f * (2.f * zz - xx - yy) + bSH_C3[4] * SHc(12) * 4.f * 2.f * xz +
-                               bSH_C3[5] * SHc(13) * (xx - yy);
+                    w[k] = sv[3 * k] * dRGB[0] + sv[3 * k + 1] * dRGB[1] + sv[3 * k + 2] * dRGB[2];
+                    if (!COMPACT) {
+                        dsh[3 * k + 0] = bs[k] * dRGB[0];
+                        dsh[3 * k + 1] = bs[k] * dRGB[1];
+                        dsh[3 * k + 2] = bs[k] * dRGB[2];
                     }
+                } else {
+                    w[k] = 0.f;
                 }
-#undef SHc
-                ddx += dx_ * dRGB[ch]; ddy += dy_ * dRGB[ch]; ddz += dz_ * dRGB[ch];
             }
-        } else {
+            if (!COMPACT) for (int k = nb; k < M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+            sh_dir_gradient(D, x, y, z, w, ddx, ddy, ddz);
+        } else if (!COMPACT) {
             for (int k = 0; k < 3 * M; ++k) dsh[k] = 0.f;
         }
-        // d normalize(v)/dv applied to dL/d(dir)  (auxiliary.h:103-114)
+        // adjoint of dir = o / |o| (auxiliary.h:103-114): (I |o|^2 - o o^T) / |o|^3 applied to dL/d(dir)
         const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
         dmx += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
         dmy += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
         dmz += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
     }
-    dL_dmeans3D[3 * idx] = dmx; dL_dmeans3D[3 * idx + 1] = dmy; dL_dmeans3D[3 * idx + 2] = dmz;
 
-    // ---- cov3D backward (backward.cu:257-310) ------------------------------------------------------
+    // ---- cov3D backward (computeCov3D's adjoint, backward.cu:257-310): Sigma = M^T M, M = S R ------------------------
+    float ds[3];
+    float4 dq;
     {
         const float sv[3] = {mod * s0, mod * s1, mod * s2};
-        const float r = q.x, x = q.y, y = q.z, z = q.w;
         const float dS[9] = {dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
                              0.5f * dcov[2], 0.5f * dcov[4], dcov[5]};
         float dMt[9];   // dMt[3j+k] = dL_dM[k][j] with dL_dM = 2*M*dL_dSigma (column-major sense)
@@ -222,20 +204,14 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
 #pragma unroll
             for (int j = 0; j < 3; ++j)
                 dMt[3 * j + k] = 2.f * c3.M[j] * dS[3 * k] + 2.f * c3.M[3 + j] * dS[3 * k + 1] + 2.f * c3.M[6 + j] * dS[3 * k + 2];
-        float ds[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) ds[j] = c3.R[j] * dMt[3 * j] + c3.R[3 + j] * dMt[3 * j + 1] + c3.R[6 + j] * dMt[3 * j + 2];
+        float G[9];     // G[3i+j] = dL/dR_ij of the rotation matrix R(q): row j of dL_dM scaled by s_j, transposed
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) dMt[3 * j + k] *= sv[j];
-#define DMT(a_, b_) dMt[3 * (a_) + (b_)]
-        float4 dq;
-        dq.x = 2 * z * (DMT(0, 1) - DMT(1, 0)) + 2 * y * (DMT(2, 0) - DMT(0, 2)) + 2 * x * (DMT(1, 2) - DMT(2, 1));
-        dq.y = 2 * y * (DMT(0, 1) + DMT(1, 0)) + 2 * z * (DMT(2, 0) + DMT(0, 2)) + 2 * r * (DMT(1, 2) - DMT(2, 1)) - 4 * x * (DMT(2, 2) + DMT(1, 1));
-        dq.z = 2 * x * (DMT(0, 1) + DMT(1, 0)) + 2 * r * (DMT(2, 0) - DMT(0, 2)) + 2 * z * (DMT(1, 2) + DMT(2, 1)) - 4 * y * (DMT(2, 2) + DMT(0, 0));
-        dq.w = 2 * r * (DMT(0, 1) - DMT(1, 0)) + 2 * x * (DMT(2, 0) + DMT(0, 2)) + 2 * y * (DMT(1, 2) + DMT(2, 1)) - 4 * z * (DMT(1, 1) + DMT(0, 0));
-#undef DMT
+            for (int k = 0; k < 3; ++k) G[3 * k + j] = dMt[3 * j + k] * sv[j];
+        dq = quat_gradient(q, G);
         if (lambda_erank > 0.f) {   // effective-rank regulariser, backward.cu:358-375 (off in every shipped config)
             const float s1s1 = s0 * s0, s2s2 = s1 * s1, s3s3 = s2 * s2, sum = s1s1 + s2s2 + s3s3;
             const float q1 = s0 / sum, q2 = s1 / sum, q3 = s2 / sum;
@@ -250,11 +226,44 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means,
             }
             ds[2] += 1.f;           // backward.cu:374 adds this unconditionally; kept for parity
         }
+    }
+    if (!COMPACT) {
+        dL_dmeans3D[3 * idx] = dmx; dL_dmeans3D[3 * idx + 1] = dmy; dL_dmeans3D[3 * idx + 2] = dmz;
         dL_dscales[3 * idx] = ds[0]; dL_dscales[3 * idx + 1] = ds[1]; dL_dscales[3 * idx + 2] = ds[2];
         dL_drots[idx] = dq;
+    } else {
+        // chain rule of the activations (same expressions as activations_backward_kernel, model_step.cu):
+        //   sigmoid' = o (1 - o);  exp' = exp;  normalize: (g - q (q.g)) / |r|
+        const float o = cg.opacity[idx];
+        const float g_o = cg.dL_dopacity[idx] * (o * (1.0f - o));
+        const float g_s0 = ds[0] * s0, g_s1 = ds[1] * s1, g_s2 = ds[2] * s2;
+        const float4 r = cg.rot_raw[idx];
+        const float nn = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+        float4 g_r;
+        if (nn > 1e-12f) {
+            const float inv = 1.0f / nn;
+            const float4 qn = make_float4(r.x * inv, r.y * inv, r.z * inv, r.w * inv);
+            const float qg = qn.x * dq.x + qn.y * dq.y + qn.z * dq.z + qn.w * dq.w;
+            g_r = make_float4((dq.x - qn.x * qg) * inv, (dq.y - qn.y * qg) * inv, (dq.z - qn.z * qg) * inv, (dq.w - qn.w * qg) * inv);
+        } else {
+            const float inv = 1.0f / 1e-12f;
+            g_r = make_float4(dq.x * inv, dq.y * inv, dq.z * inv, dq.w * inv);
+        }
+        if (cg.accumulate) {
+            cg.g_xyz[3 * idx] += dmx; cg.g_xyz[3 * idx + 1] += dmy; cg.g_xyz[3 * idx + 2] += dmz;
+            cg.g_scale[3 * idx] += g_s0; cg.g_scale[3 * idx + 1] += g_s1; cg.g_scale[3 * idx + 2] += g_s2;
+            const float4 old = cg.g_rot[idx];
+            cg.g_rot[idx] = make_float4(old.x + g_r.x, old.y + g_r.y, old.z + g_r.z, old.w + g_r.w);
+            cg.g_opacity[idx] += g_o;
+        } else {
+            cg.g_xyz[3 * idx] = dmx; cg.g_xyz[3 * idx + 1] = dmy; cg.g_xyz[3 * idx + 2] = dmz;
+            cg.g_scale[3 * idx] = g_s0; cg.g_scale[3 * idx + 1] = g_s1; cg.g_scale[3 * idx + 2] = g_s2;
+            cg.g_rot[idx] = g_r;
+            cg.g_opacity[idx] = g_o;
+        }
     }
     }   // visible
-    if (staged) warp_store_rows(dL_dsh, (size_t)wfirst, wcnt, K, slab, lane);
+    if (!COMPACT && staged) warp_store_rows(dL_dsh, (size_t)wfirst, wcnt, K, slab, lane);
 }
 
 int launch_preprocess_backward(int P, int D, int M, const float* means, const float* scales, float mod,
@@ -262,10 +271,21 @@ int launch_preprocess_backward(int P, int D, int M, const float* means, const fl
                                float lambda_erank, const float* dL_dmean2D, const float* dL_dconic,
                                const float* dL_dcolors, float* dL_dmeans3D, float* dL_dcov3D, float* dL_ddc,
                                float* dL_dsh, float* dL_dscales, float* dL_drots, cudaStream_t s) {
-    preprocess_backward_kernel<<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
+    preprocess_backward_kernel<false><<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
         P, D, M, means, scales, mod, reinterpret_cast<const float4*>(rots), sh, vp, radii, g.clamped, lambda_erank,
         dL_dmean2D, dL_dconic, dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh, dL_dscales,
-        reinterpret_cast<float4*>(dL_drots));
+        reinterpret_cast<float4*>(dL_drots), CompactGrads{});
+    GLIC_LAUNCH_CHECK();
+    return GLIC_OK;
+}
+
+int launch_preprocess_backward_compact(int P, int D, int M, const float* means, const float* scales, float mod,
+                                       const float* rots, const float* sh, const ViewParams& vp, const int* radii, GeomState g,
+                                       const float* dL_dmean2D, const float* dL_dconic, const float* dL_dcolors,
+                                       const CompactGrads& cg, cudaStream_t s) {
+    preprocess_backward_kernel<true><<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
+        P, D, M, means, scales, mod, reinterpret_cast<const float4*>(rots), sh, vp, radii, g.clamped, 0.0f,
+        dL_dmean2D, dL_dconic, dL_dcolors, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, cg);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

@@ -11,6 +11,7 @@
 // per tile instead of the reference's 18 per channel, ~3x fewer shared-memory loads than one-output-per-
 // thread, no scratch-buffer re-zeroing.  Zero ("same") padding as the reference.
 #include "common.cuh"
+#include <algorithm>
 
 namespace glic {
 
@@ -261,5 +262,68 @@ extern "C" int glic_l1_ssim_loss(int CH, int H, int W, float lambda_dssim, const
                                                           (1.0f - lambda_dssim) * inv_n);
         GLIC_LAUNCH_CHECK();
     }
+    return GLIC_OK;
+}
+
+
+// ---- evaluation metrics (evaluateVisualQuality, gaussian.cpp:756-760,795-799; loss_utils.h:35-39,84-127) --------------
+namespace glic {
+namespace {
+
+// clamp both images to [0,1] (gaussian.cpp:756-757) into scratch copies and accumulate the squared error
+__global__ void __launch_bounds__(256)
+eval_clamp_mse_kernel(size_t N, const float* __restrict__ img, const float* __restrict__ gt, float* __restrict__ a,
+                      float* __restrict__ b, double* __restrict__ acc2) {
+    double se = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = fminf(fmaxf(img[i], 0.f), 1.f), y = fminf(fmaxf(gt[i], 0.f), 1.f);
+        a[i] = x; b[i] = y;
+        const float d = x - y;
+        se += (double)(d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if ((threadIdx.x & 31) == 0 && se != 0.0) atomicAdd(&acc2[0], se);
+}
+
+__global__ void __launch_bounds__(256)
+eval_sum_kernel(size_t N, const float* __restrict__ map, double* __restrict__ acc2) {
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) s += (double)map[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc2[1], s);
+}
+
+__global__ void eval_finish_kernel(size_t N, const double* __restrict__ acc2, float* __restrict__ out2) {
+    const float mse = (float)(acc2[0] / (double)N);
+    out2[0] = 10.0f * log10f(1.0f / mse);          // loss_utils.h:35-39
+    out2[1] = (float)(acc2[1] / (double)N);        // ssim_map.mean(), loss_utils.h:107
+}
+
+}  // namespace
+}  // namespace glic
+
+extern "C" size_t glic_eval_scratch_bytes(int CH, int H, int W) { return sizeof(float) * 3 * (size_t)CH * H * W + 256; }
+
+extern "C" int glic_eval_psnr_ssim(int CH, int H, int W, const float* img, const float* gt, float* out2, void* scratch,
+                                   size_t scratch_bytes, void* stream) {
+    if (CH <= 0 || H <= 0 || W <= 0 || !img || !gt || !out2 || !scratch) { set_error("eval_psnr_ssim: bad arguments"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (scratch_bytes < glic_eval_scratch_bytes(CH, H, W)) { set_error("eval_psnr_ssim: scratch too small"); return GLIC_ERR_WORKSPACE; }
+    const size_t N = (size_t)CH * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* acc2 = static_cast<double*>(scratch);                     // first 256 bytes: the two accumulators
+    float* a = reinterpret_cast<float*>(static_cast<char*>(scratch) + 256);
+    float* b = a + N;
+    float* map = b + N;
+    GLIC_CUDA_TRY(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s));
+    const unsigned blocks = (unsigned)std::min<size_t>((N + 255) / 256, (size_t)148 * 8);
+    eval_clamp_mse_kernel<<<blocks, 256, 0, s>>>(N, img, gt, a, b, acc2);
+    GLIC_LAUNCH_CHECK();
+    if (int e = glic_fused_ssim(1, CH, H, W, 0.01f * 0.01f, 0.03f * 0.03f, a, b, map, nullptr, nullptr, nullptr, stream)) return e;
+    eval_sum_kernel<<<blocks, 256, 0, s>>>(N, map, acc2);
+    GLIC_LAUNCH_CHECK();
+    eval_finish_kernel<<<1, 1, 0, s>>>(N, acc2, out2);
+    GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

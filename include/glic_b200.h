@@ -288,6 +288,111 @@ GLIC_API int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, u
                                   float* exp_avg_sq, const float* lr6_host, float b1, float b2, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Evaluation metrics (evaluateVisualQuality, gaussian.cpp:721-830 with loss_utils.h:35-39,
+ * 84-127): both images are clamped to [0,1]; PSNR = 10 log10(1 / mean((a-b)^2)); SSIM = mean of the 11x11 /
+ * sigma 1.5 zero-padded SSIM map (the conv2d formulation, same window as the fused kernel).  out2[0] = PSNR,
+ * out2[1] = SSIM (device floats).  scratch: glic_eval_scratch_bytes.  LPIPS stays TorchScript (out of scope).
+ * ------------------------------------------------------------------------------------- */
+GLIC_API size_t glic_eval_scratch_bytes(int CH, int H, int W);
+GLIC_API int glic_eval_psnr_ssim(int CH, int H, int W, const float* img, const float* gt, float* out2, void* scratch,
+                                 size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Capacity-laid-out model arena (replaces the torch::cat re-allocation of all parameters and Adam
+ * state in GaussianModel::densificationPostfix, gaussian.cpp:426-497).  Same planar group order as the packed model,
+ * but the group offsets come from the CAPACITY:  rotation[4*Pcap] | xyz[3*Pcap] | log-scale[3*Pcap] | opacity[Pcap] |
+ * dc[3*Pcap] | sh-rest[3M*Pcap]  (glic_packed_offsets(Pcap, M)); rows [0, P) of every group are live.  Appending n rows
+ * writes rows [P, P+n) in place (Adam moments of the new rows = 0, sh-rest = 0, like the zeros_like extension tensors);
+ * growing copies the six live prefixes into an arena of a larger capacity.  Pcap must be a multiple of 4.
+ * ------------------------------------------------------------------------------------- */
+GLIC_API int glic_arena_append(float* params, float* exp_avg, float* exp_avg_sq, uint32_t P, uint32_t Pcap, uint32_t M,
+                               uint32_t n_new, const float* xyz, const float* f_dc, const float* log_scale, const float* rot,
+                               const float* opacity_logit, void* stream);
+GLIC_API int glic_arena_regrow(const float* src, uint32_t Pcap_src, float* dst, uint32_t Pcap_dst, uint32_t M, uint32_t P,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Native mapping host: the C++ counterpart of GaussianModel + extend() + optimize() +
+ * evaluateVisualQuality() + saveMap() (gaussian.cpp:113-830) on top of the kernels above -- one object per GPU, no
+ * torch, no Python.  The mapper OWNS its device memory (arena, Adam state, workspaces, keyframe images stay pinned on
+ * the host like Camera::original_image_, gaussian.cpp:80): it is the host of the loop, not an operator.
+ *
+ *   create -> initialize(raw parameters) -> { add_keyframe -> [extend] -> optimize }* -> evaluate / save_map
+ *
+ * One iteration (gaussian.cpp:674-716) = for each of this rank's views: H2D of the pinned image (copy stream,
+ * double-buffered), fused activations, forward (capacity-sized binning, no host sync), fused L1/D-SSIM loss, backward
+ * with the activation chain rule fused in; then ONE masked Adam launch.  Gradients never exist as [P,59]: the
+ * backward leaves 11 geometric floats (rotation, xyz, log-scale, opacity logit; summed over the rank's views) plus the
+ * clamp-masked dL/dcolour (3 floats) of every view, and the Adam kernel rebuilds dL/d(dc, sh-rest) -- linear in
+ * dL/dcolour with a per-view SH basis -- on the fly.  With world > 1 (view-sharded data parallelism) the
+ * exchange step moves exactly that compact form over NVLink peer memory: colour gradients are pushed to every peer while
+ * the per-Gaussian backward still runs, the 11 geometric floats are mean-reduced by the two-shot kernel; every replica
+ * then applies the identical Adam step (replicas stay bit-identical).  Semantics: mean of the per-view losses over all
+ * world * views_per_rank views, one optimiser step per batch.
+ * All host pointers unless stated.  Status codes as everywhere; the mapper never throws.
+ * ------------------------------------------------------------------------------------- */
+typedef struct glic_mapper glic_mapper;
+
+typedef struct glic_mapper_config {
+    int width, height;
+    float fx, fy, cx, cy;          /* pinhole intrinsics of every keyframe (mapping.h:53-118 Params) */
+    int sh_degree;                 /* 0..3; M = (sh_degree+1)^2 - 1 */
+    float position_lr, feature_lr, opacity_lr, scaling_lr, rotation_lr;  /* config/fastlivo.yaml:18-22; sh-rest: feature_lr/20 */
+    float lambda_dssim;            /* 0.2 */
+    float scaling_scale;           /* extend(): log(scaling_scale * depth / focal), gaussian.cpp:623 */
+    uint32_t capacity;             /* initial arena capacity in Gaussians (doubles when an append does not fit; fixed when world > 1) */
+    int max_iters;                 /* optimize(): 100 (gaussian.cpp:645) */
+    uint64_t seed;                 /* view sampler (the reference seeds from std::random_device) */
+    int rank, world;               /* world > 1: call glic_mapper_export / glic_mapper_connect before the first iteration */
+    int views_per_rank;            /* views each rank renders per iteration (gradient accumulation); >= 1 */
+} glic_mapper_config;
+
+typedef struct glic_keyframe {     /* Camera (camera.h:38-110): pose of the camera in the world + its image */
+    float R_wc[9];                 /* row-major */
+    float t_wc[3];
+    const float* image;            /* [3,H,W] in [0,1], host memory that stays valid (pinned => asynchronous H2D) */
+} glic_keyframe;
+
+typedef struct glic_mapper_stats {
+    uint32_t num_gaussians, capacity;
+    uint64_t iterations;           /* optimiser steps so far */
+    uint32_t last_inserted;        /* Gaussians appended by the last extend() */
+    float last_loss;               /* mean loss of the last iteration's local views */
+    double mean_visible;           /* optimize()'s return value: mean #visible Gaussians per iteration (gaussian.cpp:719) */
+    uint32_t overflow_regrows;     /* times the binning capacity had to grow (the frame is redone) */
+    float ms_extend, ms_optimize;  /* device time of the last extend() / optimize() */
+} glic_mapper_stats;
+
+GLIC_API int glic_mapper_create(const glic_mapper_config* cfg, glic_mapper** out);
+GLIC_API int glic_mapper_destroy(glic_mapper* m);
+/* raw parameters (host): xyz[P,3] f_dc[P,3] f_rest[P,M,3] (may be NULL: zeros) opacity_logit[P] log_scale[P,3] rot[P,4] */
+GLIC_API int glic_mapper_initialize(glic_mapper* m, uint32_t P, const float* xyz, const float* f_dc, const float* f_rest,
+                                    const float* opacity_logit, const float* log_scale, const float* rot);
+GLIC_API int glic_mapper_add_keyframe(glic_mapper* m, const glic_keyframe* kf, int is_train);
+/* extend() (gaussian.cpp:499-638) on the newest training keyframe: alpha-only render, z-buffer de-duplication of the n
+ * LiDAR points, filter, initialisation, in-place append.  points[n,3] colors[n,3] depth_rsp[n] are host arrays. */
+GLIC_API int glic_mapper_extend(glic_mapper* m, int n, const float* points, const float* colors, const float* depth_rsp);
+/* optimize() (gaussian.cpp:640-719): view sampler (all keyframes when <= max_iters, else a random subset; shuffled),
+ * then one iteration per sampled view batch.  views_host (optional, n_views entries) overrides the sampler. */
+GLIC_API int glic_mapper_optimize(glic_mapper* m, const int* views_host, int n_views);
+/* the sampler alone (tests): writes up to max_iters keyframe indices, returns their number in *count */
+GLIC_API int glic_mapper_sample_views(glic_mapper* m, int* views_host, int* count);
+/* PSNR / SSIM of one keyframe (train = 1: training list, 0: held-out list); synchronises */
+GLIC_API int glic_mapper_evaluate(glic_mapper* m, int is_train, int index, float* psnr, float* ssim);
+GLIC_API int glic_mapper_save_map(glic_mapper* m, const char* path);
+GLIC_API int glic_mapper_stats_get(glic_mapper* m, glic_mapper_stats* out);
+/* live rows of the arena copied to host arrays shaped like glic_mapper_initialize's (any pointer may be NULL); synchronises */
+GLIC_API int glic_mapper_download(glic_mapper* m, float* xyz, float* f_dc, float* f_rest, float* opacity_logit,
+                                  float* log_scale, float* rot, float* exp_avg_packed, float* exp_avg_sq_packed);
+/* multi-GPU wiring: every rank exports the 64-byte IPC handle of its exchange block, the caller all-gathers them
+ * (torch.distributed / MPI / a file: plumbing) and hands all `world` handles back. */
+GLIC_API int glic_mapper_export(glic_mapper* m, unsigned char* handle64);
+GLIC_API int glic_mapper_connect(glic_mapper* m, const unsigned char* handles /* [world][64] */);
+/* device time [ms] of the last iteration's stages {h2d_wait, activations, forward, loss, backward, exchange, adam} when
+ * profiling was enabled with glic_profile_enable */
+GLIC_API int glic_mapper_synchronize(glic_mapper* m);
+
+/* ---------------------------------------------------------------------------------------
  * Stage timing (cudaEvent pairs recorded on the launching stream around each stage; off by
  * default).  glic_profile_enable(1) starts recording and resets the accumulators;
  * glic_profile_read() synchronises the recorded events and returns, per stage, the summed

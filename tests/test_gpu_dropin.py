@@ -1,0 +1,95 @@
+"""The REAL drop-in: the reference's UNCHANGED host code -- the autograd Function of
+src/rasterizer/rasterizer.cpp:21-216, FusedSSIMMap / l1_loss of src/loss_utils.h:30-33,135-193 and
+SparseGaussianAdam of src/optim_utils.h:69-137 -- compiled from /root/reference in the authoring container and linked
+against OUR libraries (oracle/_ref/glic_dropin_ext.so, recipe oracle/ref_build/build_dropin.py), driven side by side
+with the same host code linked against the reference's own CUDA sources (oracle/_ref/glic_ref_ext.so).
+
+One mapping-iteration body (gaussian.cpp:674-716): activations (torch ops) -> rasterizer autograd op -> 0.8 L1 +
+0.2 (1 - fused SSIM) -> loss.backward() -> SparseGaussianAdam step.  Compared: image, radii, loss, the six parameter
+gradients after autograd's activation backward, and the six parameter tensors after the optimiser step.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from helpers import POSES, grad_close, small_scene
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORDER = ("means", "dc", "sh", "op", "log_s", "rot")                     # trainingSetup order, gaussian.cpp:399-424
+LRS = [1.6e-4, 2.5e-3, 2.5e-3 / 20.0, 0.05, 0.005, 0.001]               # config/fastlivo.yaml:18-22
+
+
+@pytest.fixture(scope="module")
+def dropin_ext():
+    path = os.path.join(ROOT, "oracle", "_ref", "glic_dropin_ext.so")
+    if not os.path.isfile(path):
+        pytest.skip("oracle/_ref/glic_dropin_ext.so not built (needs /root/reference at build time)")
+    import gaussian_lic_b200.ops as ops
+    ops.shim()                                                            # glic_b200_torch.so must be resident first
+    spec = importlib.util.spec_from_file_location("glic_dropin_ext", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _params(g, P):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+    return dict(means=t(g["means"]).requires_grad_(True), log_s=t(g["log_scales"]).requires_grad_(True),
+                rot=t(g["rots_raw"] if "rots_raw" in g else g["rots"]).requires_grad_(True),
+                op=t(g["opacity_logits"]).view(P, 1).requires_grad_(True), dc=t(g["dc"]).view(P, 1, 3).requires_grad_(True),
+                sh=t(g["sh"]).requires_grad_(True))
+
+
+def _iteration(ext, params, cam, gt, deg, P, H, W, step=True):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+    lims = [float(x) for x in cam["lims"]]
+    bg = torch.zeros(3, device="cuda")
+    means2D = torch.zeros_like(params["means"], requires_grad=True)                      # renderer.cpp:29
+    col, rad, _ = ext.autograd_rasterize(params["means"], means2D, torch.sigmoid(params["op"]), params["dc"], params["sh"],
+                                         torch.exp(params["log_s"]), torch.nn.functional.normalize(params["rot"]), bg,
+                                         t(cam["view"]).view(4, 4), t(cam["proj"]).view(4, 4), t(cam["campos"]), H, W,
+                                         cam["tanfovx"], cam["tanfovy"], lims[0], lims[1], lims[2], lims[3], deg, False, 0.0)
+    loss = 0.8 * ext.l1_autograd(col, gt) + 0.2 * (1.0 - ext.fused_ssim_autograd(col.unsqueeze(0), gt.unsqueeze(0)))
+    loss.backward()
+    grads = {k: params[k].grad.detach().clone() for k in params}
+    if step:
+        ext.sparse_adam_step([params[k] for k in ORDER], LRS, rad > 0, P)
+    torch.cuda.synchronize()
+    return col.detach(), rad, float(loss.item()), grads
+
+
+@pytest.mark.parametrize("view,pp", POSES[:4])
+@pytest.mark.parametrize("P,W,H,deg,seed", [(4096, 320, 208, 3, 11), (10240, 640, 480, 0, 42)])
+def test_dropin_iteration_matches_reference(ref_ext, dropin_ext, P, W, H, deg, seed, view, pp):
+    from gaussian_lic_b200 import synthetic as syn
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
+    gt = torch.as_tensor(syn.make_gt_image(W, H)).cuda()
+    pa, pb = _params(g, P), _params(g, P)
+    col_a, rad_a, loss_a, ga = _iteration(dropin_ext, pa, cam, gt, deg, P, H, W)
+    col_b, rad_b, loss_b, gb = _iteration(ref_ext, pb, cam, gt, deg, P, H, W)
+    assert torch.equal(rad_a, rad_b)
+    assert (col_a - col_b).abs().max().item() <= 1e-4
+    assert abs(loss_a - loss_b) <= 2e-6, (loss_a, loss_b)
+    for k in ga:
+        if ga[k].numel():
+            grad_close(ga[k].cpu().numpy(), gb[k].cpu().numpy(), "drop-in d%s vs reference" % k, rtol=5e-4)
+    # the first Adam step moves every visible element by lr * g/(|g| + eps) ~ +-lr: parameters agree to a few ulp except
+    # where the gradient itself is at rounding-noise level (its sign is then arbitrary in both builds)
+    vis = (rad_b > 0)
+    for k, lr in zip(ORDER, LRS):
+        a, b = pa[k].detach(), pb[k].detach()
+        assert torch.equal(a[~vis], b[~vis]), k                       # invisible Gaussians: untouched, bit for bit
+        noise = gb[k].abs() <= 1e-4 * gb[k].abs().max()
+        d = (a - b).abs()
+        assert d[~noise].max().item() <= 0.05 * lr + 1e-7, (k, d[~noise].max().item(), lr)
+        assert d.max().item() <= 2.0 * lr * 1.001 + 1e-7, (k, d.max().item())
+
+
+def test_dropin_distcuda2(ref_ext, dropin_ext):
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    pts = torch.randn(30_000, 3, device="cuda", generator=gen) * 4.0
+    torch.testing.assert_close(dropin_ext.distCUDA2(pts), ref_ext.distCUDA2(pts), rtol=2e-6, atol=0)
