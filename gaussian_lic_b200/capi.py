@@ -23,6 +23,24 @@ class View(C.Structure):
                 ("width", C.c_int), ("height", C.c_int)]
 
 
+class MapperConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("sh_degree", C.c_int), ("position_lr", C.c_float), ("feature_lr", C.c_float), ("opacity_lr", C.c_float),
+                ("scaling_lr", C.c_float), ("rotation_lr", C.c_float), ("lambda_dssim", C.c_float), ("scaling_scale", C.c_float),
+                ("capacity", C.c_uint32), ("max_iters", C.c_int), ("seed", C.c_uint64), ("rank", C.c_int), ("world", C.c_int),
+                ("views_per_rank", C.c_int)]
+
+
+class Keyframe(C.Structure):
+    _fields_ = [("R_wc", C.c_float * 9), ("t_wc", C.c_float * 3), ("image", C.c_void_p)]
+
+
+class MapperStats(C.Structure):
+    _fields_ = [("num_gaussians", C.c_uint32), ("capacity", C.c_uint32), ("iterations", C.c_uint64), ("last_inserted", C.c_uint32),
+                ("last_loss", C.c_float), ("mean_visible", C.c_double), ("overflow_regrows", C.c_uint32), ("ms_extend", C.c_float),
+                ("ms_optimize", C.c_float)]
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
@@ -81,6 +99,25 @@ def _load():
         "glic_p2p_free": (i32, [vp]),
         "glic_p2p_allreduce_mean": (i32, [i32, i32, C.POINTER(vp), sz, sz, vp]),
         "glic_p2p_check": (i32, [vp, sz, sz, vp]),
+        "glic_eval_scratch_bytes": (sz, [i32, i32, i32]),
+        "glic_eval_psnr_ssim": (i32, [i32, i32, i32, vp, vp, vp, vp, sz, vp]),
+        "glic_arena_append": (i32, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp]),
+        "glic_arena_regrow": (i32, [vp, u32, vp, u32, u32, u32, vp]),
+        "glic_camera_block": (i32, [i32, i32, f32, f32, f32, f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
+        "glic_mapper_create": (i32, [C.POINTER(MapperConfig), C.POINTER(vp)]),
+        "glic_mapper_destroy": (i32, [vp]),
+        "glic_mapper_initialize": (i32, [vp, u32, vp, vp, vp, vp, vp, vp]),
+        "glic_mapper_add_keyframe": (i32, [vp, C.POINTER(Keyframe), i32]),
+        "glic_mapper_extend": (i32, [vp, i32, vp, vp, vp]),
+        "glic_mapper_optimize": (i32, [vp, C.POINTER(i32), i32]),
+        "glic_mapper_sample_views": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "glic_mapper_evaluate": (i32, [vp, i32, i32, C.POINTER(f32), C.POINTER(f32)]),
+        "glic_mapper_save_map": (i32, [vp, C.c_char_p]),
+        "glic_mapper_stats_get": (i32, [vp, C.POINTER(MapperStats)]),
+        "glic_mapper_download": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "glic_mapper_export": (i32, [vp, C.c_char_p]),
+        "glic_mapper_connect": (i32, [vp, C.c_char_p]),
+        "glic_mapper_synchronize": (i32, [vp]),
         "glic_debug_geom": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_debug_binning": (i32, [i32, vp, i64, i64, vp, vp, vp, vp]),
         "glic_debug_image": (i32, [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp]),

@@ -290,7 +290,7 @@ extern "C" int glic_backward_compact_internal(int P, int sh_degree, int M, const
 namespace glic {
 int launch_adam_compact(uint32_t P, uint32_t Pcap, int D, int M, float* params, float* exp_avg, float* exp_avg_sq, const float* g_geo,
                         uint32_t Pcap_geo, const float* lr6, const float* g_color, const uint8_t* flags, const float* campos4,
-                        int n_slots, float grad_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
+                        int n_slots, float grad_scale, float color_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
                         unsigned int* visible_count, cudaStream_t s);
 int launch_view_flags(int P, const int* radii, const GeomState& g, uint8_t* flags, cudaStream_t s);
 }  // namespace glic

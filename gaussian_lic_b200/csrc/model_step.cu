@@ -101,7 +101,7 @@ struct ArenaLayout {
 struct ViewSlots {
     const float* g_color;    // [n_slots][stride][3] dL/dcolour per view as the render backward left it (before the clamp mask)
     const uint8_t* visible;  // [n_slots][stride] per-view flags: 0x80 = radii > 0, bits 0..2 = colour channel clamped (forward.cu:70-75)
-    const float* campos;     // [n_slots][4]
+    float campos[32 * 4];    // [n_slots][4] camera centres of the batch's views, by value (n_slots <= 32)
     size_t stride;           // Gaussians per slot (the arena capacity)
     int n_slots;
 };
@@ -111,7 +111,7 @@ constexpr int ADAM_WARPS = 4;
 __global__ void __launch_bounds__(ADAM_WARPS * 32)
 adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                     const float* __restrict__ g_geo /* arena-shaped: rotation | xyz | log-scale | opacity */, ArenaLayout L,
-                    ArenaLayout Lg, ViewSlots vs, float grad_scale, float b1, float b2, float eps,
+                    ArenaLayout Lg, ViewSlots vs, float grad_scale, float color_scale, float b1, float b2, float eps,
                     const unsigned int* __restrict__ skip_flag, unsigned int* __restrict__ visible_count) {
     __shared__ float s_g[ADAM_WARPS][32 * SH_ROW_MAX];
     __shared__ uint8_t s_vis[ADAM_WARPS][32];
@@ -156,7 +156,7 @@ adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float*
             }
         }
 #pragma unroll
-        for (int k = 0; k < SH_ROW_MAX; ++k) if (k < K) slab[lane * K + k] = acc[k] * grad_scale;
+        for (int k = 0; k < SH_ROW_MAX; ++k) if (k < K) slab[lane * K + k] = acc[k] * color_scale;
         // ---- geometric groups + dc: 14 scalars per Gaussian ----
         auto step = [&](int grp, int kk, size_t j, float g) {
             const size_t e = L.off[grp] + j;
@@ -173,7 +173,7 @@ adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float*
         for (int c = 0; c < 3; ++c) step(2, 3, 3 * (size_t)i + c, g_geo[Lg.off[2] + 3 * (size_t)i + c] * grad_scale);
         step(3, 1, (size_t)i, g_geo[Lg.off[3] + (size_t)i] * grad_scale);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) step(4, 3, 3 * (size_t)i + c, gdc[c] * grad_scale);
+        for (int c = 0; c < 3; ++c) step(4, 3, 3 * (size_t)i + c, gdc[c] * color_scale);
     }
     if (K == 0) return;
     __syncwarp();
@@ -333,7 +333,7 @@ int launch_view_flags(int P, const int* radii, const GeomState& g, uint8_t* flag
 
 int launch_adam_compact(uint32_t P, uint32_t Pcap, int D, int M, float* params, float* exp_avg, float* exp_avg_sq, const float* g_geo,
                         uint32_t Pcap_geo, const float* lr6, const float* g_color, const uint8_t* flags, const float* campos4,
-                        int n_slots, float grad_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
+                        int n_slots, float grad_scale, float color_scale, float b1, float b2, float eps, const unsigned int* skip_flag,
                         unsigned int* visible_count, cudaStream_t s) {
     if (P == 0) return GLIC_OK;
     ArenaLayout L, Lg;
@@ -343,11 +343,13 @@ int launch_adam_compact(uint32_t P, uint32_t Pcap, int D, int M, float* params, 
     glic_packed_offsets(Pcap_geo, 0, off6);                         // geometric arena: rotation | xyz | log-scale | opacity
     for (int q = 0; q < 6; ++q) { Lg.off[q] = off6[q]; Lg.lr[q] = 0.f; }
     ViewSlots vs;
-    vs.g_color = g_color; vs.visible = flags; vs.campos = campos4; vs.stride = Pcap_geo; vs.n_slots = n_slots;
+    if (n_slots < 1 || n_slots > 32 || !campos4) { set_error("adam_compact: 1..32 view slots"); return GLIC_ERR_INVALID_ARGUMENT; }
+    vs.g_color = g_color; vs.visible = flags; vs.stride = Pcap_geo; vs.n_slots = n_slots;
+    for (int i = 0; i < 4 * n_slots; ++i) vs.campos[i] = campos4[i];
     const unsigned warps = (P + 31) / 32;
     StageTimer _t(GLIC_STAGE_ADAM, s);
     adam_compact_kernel<<<(warps + ADAM_WARPS - 1) / ADAM_WARPS, ADAM_WARPS * 32, 0, s>>>(P, D, M, params, exp_avg, exp_avg_sq, g_geo, L, Lg, vs,
-                                                                                          grad_scale, b1, b2, eps, skip_flag, visible_count);
+                                                                                          grad_scale, color_scale, b1, b2, eps, skip_flag, visible_count);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

@@ -238,7 +238,7 @@ class CRasterizer:
         self.cap_target = 0
         self.stream = None      # cudaStream_t handle (int) or None = legacy default stream
         self.counters = torch.zeros(3, dtype=torch.int64).pin_memory() if torch.cuda.is_available() else torch.zeros(3, dtype=torch.int64)
-        self._view_keep = None
+        self._view_keep = []    # device tensors behind every View handed out (a View only holds raw pointers)
 
     def _grow(self, name, nbytes, slack=1.25):
         t = getattr(self, name)
@@ -254,7 +254,7 @@ class CRasterizer:
         lims = [float(x) for x in cam["lims"]]
         view = capi.View(v.data_ptr(), p.data_ptr(), c.data_ptr(), cam["tanfovx"], cam["tanfovy"], lims[0], lims[1],
                          lims[2], lims[3], self.W, self.H)
-        self._view_keep = (v, p, c)
+        self._view_keep.append((v, p, c))
         return view
 
     def forward(self, g, view, no_color=False, scale_modifier=1.0, out_color=None, out_T=None, radii=None, sync=True):

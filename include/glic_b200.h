@@ -357,7 +357,7 @@ typedef struct glic_mapper_stats {
     uint32_t num_gaussians, capacity;
     uint64_t iterations;           /* optimiser steps so far */
     uint32_t last_inserted;        /* Gaussians appended by the last extend() */
-    float last_loss;               /* mean loss of the last iteration's local views */
+    float last_loss;               /* loss of the last finished iteration's last local view */
     double mean_visible;           /* optimize()'s return value: mean #visible Gaussians per iteration (gaussian.cpp:719) */
     uint32_t overflow_regrows;     /* times the binning capacity had to grow (the frame is redone) */
     float ms_extend, ms_optimize;  /* device time of the last extend() / optimize() */
@@ -388,9 +388,11 @@ GLIC_API int glic_mapper_download(glic_mapper* m, float* xyz, float* f_dc, float
  * (torch.distributed / MPI / a file: plumbing) and hands all `world` handles back. */
 GLIC_API int glic_mapper_export(glic_mapper* m, unsigned char* handle64);
 GLIC_API int glic_mapper_connect(glic_mapper* m, const unsigned char* handles /* [world][64] */);
-/* device time [ms] of the last iteration's stages {h2d_wait, activations, forward, loss, backward, exchange, adam} when
- * profiling was enabled with glic_profile_enable */
 GLIC_API int glic_mapper_synchronize(glic_mapper* m);
+/* Camera (camera.h:38-110) in closed form, as the mapper derives it from a keyframe pose: out41 = view[16] (column-major
+ * Rt) | proj[16] (column-major P*Rt) | campos[3] | tan_fovx, tan_fovy | limx_neg, limx_pos, limy_neg, limy_pos. */
+GLIC_API int glic_camera_block(int width, int height, float fx, float fy, float cx, float cy, const float* R_wc /*[9] row-major*/,
+                               const float* t_wc /*[3]*/, float* out41);
 
 /* ---------------------------------------------------------------------------------------
  * Stage timing (cudaEvent pairs recorded on the launching stream around each stage; off by

@@ -44,7 +44,7 @@ def _params(g, P):
                 sh=t(g["sh"]).requires_grad_(True))
 
 
-def _iteration(ext, params, cam, gt, deg, P, H, W, step=True):
+def _iteration(ext, params, cam, gt, deg, P, H, W, step=True, empty_groups=False):
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
     lims = [float(x) for x in cam["lims"]]
     bg = torch.zeros(3, device="cuda")
@@ -57,7 +57,10 @@ def _iteration(ext, params, cam, gt, deg, P, H, W, step=True):
     loss.backward()
     grads = {k: params[k].grad.detach().clone() for k in params}
     if step:
-        ext.sparse_adam_step([params[k] for k in ORDER], LRS, rad > 0, P)
+        # an EMPTY group (sh-rest at degree 0: [P,0,3]) makes the reference launch adamUpdateCUDA with a zero-block grid
+        # (adam.cu:54: cudaErrorInvalidConfiguration, left in the error state); it is passed only when asked for
+        keep = [i for i, k in enumerate(ORDER) if params[k].numel() or empty_groups]
+        ext.sparse_adam_step([params[ORDER[i]] for i in keep], [LRS[i] for i in keep], rad > 0, P)
     torch.cuda.synchronize()
     return col.detach(), rad, float(loss.item()), grads
 
@@ -69,7 +72,7 @@ def test_dropin_iteration_matches_reference(ref_ext, dropin_ext, P, W, H, deg, s
     g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
     gt = torch.as_tensor(syn.make_gt_image(W, H)).cuda()
     pa, pb = _params(g, P), _params(g, P)
-    col_a, rad_a, loss_a, ga = _iteration(dropin_ext, pa, cam, gt, deg, P, H, W)
+    col_a, rad_a, loss_a, ga = _iteration(dropin_ext, pa, cam, gt, deg, P, H, W, empty_groups=True)   # ours tolerates the empty group
     col_b, rad_b, loss_b, gb = _iteration(ref_ext, pb, cam, gt, deg, P, H, W)
     assert torch.equal(rad_a, rad_b)
     assert (col_a - col_b).abs().max().item() <= 1e-4
@@ -77,16 +80,20 @@ def test_dropin_iteration_matches_reference(ref_ext, dropin_ext, P, W, H, deg, s
     for k in ga:
         if ga[k].numel():
             grad_close(ga[k].cpu().numpy(), gb[k].cpu().numpy(), "drop-in d%s vs reference" % k, rtol=5e-4)
-    # the first Adam step moves every visible element by lr * g/(|g| + eps) ~ +-lr: parameters agree to a few ulp except
-    # where the gradient itself is at rounding-noise level (its sign is then arbitrary in both builds)
+    # the first Adam step (no bias correction) moves every visible element by lr * 0.1 g / sqrt(0.001 g^2) = 3.16 lr * sign(g):
+    # parameters agree to a few ulp except where the gradient itself is at rounding-noise level (its sign is then arbitrary
+    # in both builds: up to 2 * 3.16 lr apart)
     vis = (rad_b > 0)
     for k, lr in zip(ORDER, LRS):
         a, b = pa[k].detach(), pb[k].detach()
+        if a.numel() == 0:
+            continue
         assert torch.equal(a[~vis], b[~vis]), k                       # invisible Gaussians: untouched, bit for bit
         noise = gb[k].abs() <= 1e-4 * gb[k].abs().max()
         d = (a - b).abs()
-        assert d[~noise].max().item() <= 0.05 * lr + 1e-7, (k, d[~noise].max().item(), lr)
-        assert d.max().item() <= 2.0 * lr * 1.001 + 1e-7, (k, d.max().item())
+        if bool((~noise).any()):                                      # dc at degree 0: the reference computes no colour gradient at all
+            assert d[~noise].max().item() <= 0.05 * lr + 1e-7, (k, d[~noise].max().item(), lr)
+        assert d.max().item() <= 6.4 * lr + 1e-7, (k, d.max().item())
 
 
 def test_dropin_distcuda2(ref_ext, dropin_ext):
