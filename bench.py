@@ -6,11 +6,15 @@
 Metric: Gaussians/s rasterised (forward + fused L1/D-SSIM loss + backward) at 1920x1080, SH degree 3
 (BASELINE.json configs[1]: 500 k Gaussians, one view per GPU).  One JSON line on stdout (rank 0).
 
-  value     : whole-job Gaussians/s with every input already resident in HBM (C ABI, persistent workspaces)
-  e2e       : the same step through the reference-facing LibTorch symbols (RasterizeGaussiansCUDA ...,
-              driven by the autograd mirror of rasterizer.cpp) with the per-iteration HOST inputs of the
+  value     : whole-job Gaussians/s with every input already resident in HBM: the native C++ mapper (csrc/mapper.cu)
+              running activations + forward + fused loss + backward (+ the NVLink exchange at N > 1), optimiser off
+  e2e       : the same step through the reference-facing LibTorch symbols (RasterizeGaussiansCUDA ...) under torch
+              autograd, called from a C++ host (csrc/torch_host.cpp), with the per-iteration HOST inputs of the
               reference loop (gaussian.cpp:674-699): pinned ground-truth image + camera H2D every step,
               loss scalar D2H every step
+  mapping_iter / mapping_iter_native : BASELINE's second half, the body of optimize()'s loop, through the LibTorch
+              symbols and through the native mapper
+  sort_cfg5 : BASELINE configs[4] (50 M key/value pairs), appended to the N = 1 line of both arms
   roofline  : dominant kernel (per-stage cudaEvent timing inside the library, on the launching stream)
   cpu_baseline : the CPU oracle (port of the reference algorithm; the reference has no CPU path) on the
               host cores, bounded sample
@@ -33,6 +37,29 @@ import numpy as np  # noqa: E402
 
 METRIC = "Gaussians/sec rasterized (fwd+bwd) @1920x1080"
 LAMBDA_DSSIM = 0.2
+
+
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Anything a library prints on fd 1 (NCCL's version banner, a stray warning) goes to stderr; the ONE JSON line is written
+    to the real stdout by emit()."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        sys.stdout.buffer.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, line)
 
 
 def load_synthetic():
@@ -191,17 +218,16 @@ def gather_ranks(ms, world):
     return [float(x.item()) for x in out]
 
 
-def timed_windows(run_step, steps, world, dev, min_windows=5, min_total_ms=500.0, max_windows=60):
-    """Device-timed windows of EXACTLY `steps` steps each.  Every window is bracketed by a barrier +
-    torch.cuda.synchronize() on both sides and timed with a CUDA event pair on the launching stream; a window's time is
-    the MAX over ranks.  The reported figure is the MEDIAN window (>= 5 windows and >= 0.5 s of timed work in total),
-    so one host-side hiccup on one rank (a 100 ms stall inside a 30 ms window was the round-1 N = 8 collapse) cannot
-    set the number; every window is returned so the spread is visible.  -> (median ms/step, [window ms/step], per-rank
-    ms/step of the median window)."""
+def timed_windows(window, steps, world, dev, min_windows=5, min_total_ms=500.0, max_windows=60):
+    """Device-timed windows of EXACTLY `steps` steps each.  `window()` runs the steps and returns the device time [ms] of
+    the whole window, measured with a CUDA event pair on the stream the steps are launched on.  Every window is bracketed
+    by a barrier + torch.cuda.synchronize() on both sides; a window's time is the MAX over ranks.  The reported figure is
+    the MEDIAN window (>= 5 windows and >= 0.5 s of timed work in total), so one host-side hiccup on one rank (a 100 ms
+    stall inside a 30 ms window was the round-1 N = 8 collapse) cannot set the number; every window is returned so the
+    spread is visible.  -> (median ms/step, [window ms/step], per-rank ms/step of the median window)."""
     import torch
     if world > 1:
         import torch.distributed as dist
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wins, ranks = [], []
     n = min_windows
     i = 0
@@ -210,14 +236,10 @@ def timed_windows(run_step, steps, world, dev, min_windows=5, min_total_ms=500.0
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
-        e0.record()
-        for _ in range(steps):
-            run_step()
-        e1.record()
+        mine = window() / steps
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
-        mine = e0.elapsed_time(e1) / steps
         wins.append(max_over_ranks(mine, world))
         ranks.append(mine)
         if i == 0:                                           # identical on every rank (max-reduced): same window count
@@ -228,317 +250,347 @@ def timed_windows(run_step, steps, world, dev, min_windows=5, min_total_ms=500.0
     return wins[mid], [round(w, 4) for w in wins], [round(x, 4) for x in gather_ranks(ranks[mid], world)]
 
 
+def torch_window(fn, steps):
+    """K calls of fn timed with a torch event pair on the current stream -> ms of the window."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run():
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    return run
+
+
+def sort_microbench(torch, ref=None, n=50_000_000, end_bit=45, reps=5):
+    """BASELINE configs[4]: n (tile|depth) key/value pairs, bits [0, 45): our CUB-free onesweep (and, in the reference arm,
+    cub::DeviceRadixSort::SortPairs as rasterizer_impl.cu:419-424 calls it) against the SURVEY 8(d) byte model."""
+    syn = load_synthetic()
+    keys_h, vals_h = syn.make_sort_pairs(n)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    keys = torch.as_tensor(keys_h.view(np.int64)).to(dev)
+    vals = torch.as_tensor(vals_h.view(np.int32)).to(dev)
+    A = (8 + 24 * ((end_bit + 7) // 8)) * n
+    peak, _ = peaks()
+    out = {"n": n, "end_bit": end_bit, "A_sort_bytes": A}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_in, v_in, k_out, v_out = keys.clone(), vals.clone(), torch.empty_like(keys), torch.empty_like(vals)
+
+    def timeit(fn):
+        ts = []
+        for _ in range(reps + 1):
+            k_in.copy_(keys); v_in.copy_(vals)
+            torch.cuda.synchronize()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts[1:]))
+
+    if ref is None:
+        from gaussian_lic_b200 import capi
+        lib = capi.lib
+        temp = torch.empty(lib.glic_sort_temp_bytes(n), dtype=torch.uint8, device=dev)
+        ms = timeit(lambda: capi.check(lib.glic_sort_pairs_u64_u32(n, end_bit, capi.ptr(k_in), capi.ptr(v_in), capi.ptr(k_out), capi.ptr(v_out),
+                                                                   capi.ptr(temp), temp.numel(), None), "sort"))
+        out.update({"impl": "own onesweep (csrc/radix_sort.cu)", "ms": round(ms, 4), "GBs": round(A / ms / 1e6, 1), "frac_of_hbm_peak": round(A / ms / 1e6 / peak, 4)})
+    else:
+        nbytes = ref.cub_sort_pairs(torch.empty(0, dtype=torch.uint8, device=dev), k_in, k_out, v_in, v_out, end_bit)
+        temp = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        ms = timeit(lambda: ref.cub_sort_pairs(temp, k_in, k_out, v_in, v_out, end_bit))
+        out.update({"impl": "cub::DeviceRadixSort::SortPairs (CUDA 12.9 CCCL)", "ms": round(ms, 4), "GBs": round(A / ms / 1e6, 1), "frac_of_hbm_peak": round(A / ms / 1e6 / peak, 4)})
+    out["checksum"] = int((k_out[::9973].sum() ^ v_out[::9973].to(torch.int64).sum()).item())     # equal in both arms iff the outputs agree on the sample
+    return out
+
+
 def run_ours(args):
     import torch
-    from gaussian_lic_b200 import capi, ops, synthetic as syn
+    from gaussian_lic_b200 import capi, ops, mapper as gmapper, synthetic as syn
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    cfg = args.config
-    P, W, H, fx, fy, cx, cy, deg, zmax = syn.CONFIGS[cfg]
-    g, _ = syn.make_scene(cfg)
-    # one training view per rank: an 8-view ring of nearby keyframes around view 0, as a sliding-window
-    # mapper would batch them; the small radius keeps the per-GPU work of the weak-scaling run within a few percent
-    view_id = (rank % 8) if args.view is None else args.view
-    R_wc, t_wc = syn.orbit_pose(view_id, radius=args.rig_radius)
-    cam = syn.make_camera(W, H, fx, fy, cx, cy, R_wc, t_wc)
-    gt_host = torch.as_tensor(syn.make_gt_image(W, H)).pin_memory()
-    gd = ops.scene_to_device(g, dev)
-    gt = gt_host.to(dev)
-    M = gd["sh"].shape[1]
-    r = ops.CRasterizer(W, H, dev)
-    view = r.make_view(cam)
-    f32 = dict(dtype=torch.float32, device=dev)
-    color, T = torch.empty(3, H, W, **f32), torch.empty(H, W, **f32)
-    radii = torch.empty(P, dtype=torch.int32, device=dev)
-    loss_out, dL = torch.empty(1, **f32), torch.empty(3, H, W, **f32)
-    grads = r.alloc_grads(P, M)
-    allreduce = None
     if world > 1:
         import torch.distributed as dist
-        from gaussian_lic_b200 import dist as gdist
-        # the exchange step: our own two-shot all-reduce over NVLink peer memory (csrc/p2p.cu); --exchange nccl keeps
-        # the library collective as the comparison
-        if args.exchange == "p2p":
-            try:
-                allreduce = gdist.P2PGradAllReduce(P, M, dev)
-            except RuntimeError as e:                          # raised on every rank together (dist.py): IPC not permitted here
-                print("[bench] %s -- falling back to the NCCL all-reduce" % (e,), file=sys.stderr)
-                args.exchange = "nccl"
-        if allreduce is None:
-            allreduce = gdist.GradAllReduce(P, M, dev)
-        grads = allreduce.grads                           # backward writes straight into the collective's buffer
+    cfg = args.config
+    P, W, H, fx, fy, cx, cy, deg, zmax = syn.CONFIGS[cfg]
+    k = max(1, args.views_per_gpu)
+    S = world * k
+    g, _ = syn.make_scene(cfg)
+    M = g["sh"].shape[1]
+    # the iteration's view batch (SURVEY 8e): slot s renders view s % 8 of an 8-view ring of nearby keyframes around view 0,
+    # as a sliding-window mapper would batch them; rank r renders slots [r*k, (r+1)*k)
+    poses = [syn.orbit_pose(v, radius=args.rig_radius) for v in range(8)]
+    gt_host = torch.as_tensor(syn.make_gt_image(W, H)).pin_memory()
+    gt = gt_host.to(dev)
+    steps = args.steps
 
-    def step():
-        r.forward(gd, view, out_color=color, out_T=T, radii=radii, sync=False)
-        r.loss(color, gt, LAMBDA_DSSIM, loss_out, dL)
-        r.backward(gd, view, radii, dL, grads)
-        if allreduce is not None:
-            allreduce(radii)
+    # ---- the product host: native mapper (csrc/mapper.cu), one per GPU ---------------------------------------------------
+    mp = gmapper.Mapper(W, H, fx, fy, cx, cy, sh_degree=deg, capacity=P, rank=rank, world=world, views_per_rank=k)
+    mp.initialize(g)
+    for R_wc, t_wc in poses:
+        mp.add_keyframe(R_wc, t_wc, gt)                       # keyframes 0..7: image RESIDENT in HBM (the `value` leg)
+    for R_wc, t_wc in poses:
+        mp.add_keyframe(R_wc, t_wc, gt_host)                  # keyframes 8..15: image in pinned host memory (H2D every iteration)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, mp.export_handle())
+        mp.connect(handles)
+        dist.barrier()
+    batch_res = [s % 8 for s in range(S)]
+    batch_host = [8 + s % 8 for s in range(S)]
 
-    r.forward(gd, view, out_color=color, out_T=T, radii=radii, sync=True)      # settles the binning capacity once
-    for _ in range(max(args.warmup, 3)):
-        step()
-    assert not r.finish(), "binning capacity overflow during warm-up"
-    V = int((radii > 0).sum().item())
-    Rn, Bn = r.R, r.B
+    def mapper_window(batch):
+        def run():
+            return mp.optimize(batch * steps).ms_optimize     # K iterations enqueued back to back, device-timed on the mapper's stream
+        return run
 
-    # ---- timed region: K steps, barrier + sync on both sides, CUDA events, max over ranks -------------
-    # CUDA-graph the step when it has no collective: forward, loss and backward contain no host synchronisation
-    # (capacity-sized binning), so ~25 launches + memsets replay as one graph launch.
-    graph = None
-    if (allreduce is None or args.exchange == "p2p") and not args.no_graph:
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                r.stream = side.cuda_stream
-                step()                                       # warm the side stream
-                side.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):
-                    r.stream = torch.cuda.current_stream(dev).cuda_stream
-                    step()
-            r.stream = None
-            torch.cuda.current_stream(dev).wait_stream(side)
-            for _ in range(3):
-                graph.replay()
-            torch.cuda.synchronize(dev)
-            assert not r.finish()
-        except Exception as e:                               # capture is an optimisation, never a requirement
-            print("[bench] CUDA graph capture unavailable: %r" % (e,), file=sys.stderr)
-            graph, r.stream = None, None
-            torch.cuda.synchronize(dev)
-    run_step = graph.replay if graph is not None else step
-    # clock sampler first (its process start must not land between the barrier and the first event), then the windows
+    # ---- value: rasterization step (activations, forward, fused loss, backward, [exchange]) on resident inputs ----------
+    mp.set_optimizer(False)
+    mp.optimize(batch_res * max(args.warmup, 3))              # warm-up; settles the binning capacity
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     l0 = capi.launch_count()
-    ms_step, windows, per_rank = timed_windows(run_step, args.steps, world, dev)
-    launches = capi.launch_count() - l0
-    if graph is not None:                                  # replays do not pass through the launch counter
-        l0 = capi.launch_count()
-        step(); torch.cuda.synchronize(dev)
-        launches = (capi.launch_count() - l0) * args.steps
-    else:
-        launches //= len(windows)
-    assert not r.finish(), "binning capacity overflow inside the timed region"
+    ms_step, windows, per_rank = timed_windows(mapper_window(batch_res), steps, world, dev)
+    launches = (capi.launch_count() - l0) // len(windows)
     clocks = sampler.stop() if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    value = P * world / (ms_step * 1e-3)
+    regrows = mp.stats().overflow_regrows
+    value = P * S / (ms_step * 1e-3)
 
-    # ---- per-stage timing for the roofline (separate pass; events on the launching stream) ---------------
+    # ---- per-stage timing for the roofline (events around each stage inside the library, on the launching stream) ---------
+    r = ops.CRasterizer(W, H, dev)
+    cam0 = gmapper.camera_block(W, H, fx, fy, cx, cy, *poses[(rank * k) % 8])
+    gd = ops.scene_to_device(g, dev)
+    _, _, radii0 = r.forward(gd, r.make_view(cam0))
+    V = int((radii0 > 0).sum().item())
+    Rn, Bn = r.R, r.B
+    del r
     capi.profile_enable(True)
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize(dev)
+    mp.optimize(batch_res * steps)
     prof = capi.profile_read()
     capi.profile_enable(False)
-    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+    stage_ms = {kk: (v[0] / v[1] if v[1] else 0.0) for kk, v in prof.items()}
+    for kk in ("sort", "zero"):                               # several recordings per view: report per view
+        if prof[kk][1]:
+            stage_ms[kk] = prof[kk][0] / (steps * k)
     A1, per_stage = algorithmic_bytes(P, V, Rn, H * W, M)
-    dom = max((k for k in stage_ms if k in per_stage), key=lambda k: stage_ms[k])
+    dom = max((kk for kk in stage_ms if kk in per_stage), key=lambda kk: stage_ms[kk])
     peak, peak_src = peaks()
     ach = per_stage[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(per_stage[dom]), "kernel_ms": round(stage_ms[dom], 4),
-                "step_algorithmic_bytes": int(A1), "step_frac": round(A1 / (ms_step * 1e-3) / 1e9 / peak, 4),
-                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items() if v > 0}}
+                "step_algorithmic_bytes": int(A1 * k), "step_frac": round(A1 * k / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "stage_ms": {kk: round(v, 4) for kk, v in stage_ms.items() if v > 0}}
     tf = os.path.join(ROOT, "profiles", "traffic_%s.json" % dom)
     if os.path.isfile(tf):
         roofline["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch")
 
     if args.kernel_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms_step, "roofline": roofline, "kernel_only": True,
+            emit(({"metric": METRIC, "value": value, "ms_per_step": ms_step, "roofline": roofline, "kernel_only": True,
                               "config": {"P": P, "V": V, "R": Rn, "B": Bn}}))
+        mp.close()
         return
-    # ---- e2e: reference-facing symbols, host inputs every step -------------------------------------------
-    t = lambda a: torch.as_tensor(a, dtype=torch.float32)
-    params = dict(means=gd["means"].clone().requires_grad_(True),
-                  log_s=t(g["log_scales"]).to(dev).requires_grad_(True),
-                  rot=gd["rots"].clone().requires_grad_(True),
-                  op=t(g["opacity_logits"]).view(-1, 1).to(dev).requires_grad_(True),
-                  dc=gd["dc"].view(P, 1, 3).clone().requires_grad_(True), sh=gd["sh"].clone().requires_grad_(True))
-    cam_host = torch.cat([t(cam["view"]), t(cam["proj"]), t(cam["campos"])]).pin_memory()
-    lims = [float(x) for x in cam["lims"]]
-    bg = torch.zeros(3, device=dev)
 
-    copy_stream = torch.cuda.Stream(dev)
+    # ---- native mapping iteration: pinned image H2D every iteration + the step above + the SH-rebuilding masked Adam --------
+    mp.set_optimizer(True)
+    mp.optimize(batch_host * 3)
+    nat_ms, nat_windows, _ = timed_windows(mapper_window(batch_host), steps, world, dev, min_windows=3, min_total_ms=200.0)
+    st = mp.stats()
+    native = {"ms_per_iter": round(nat_ms, 4), "views_per_iter": S, "loss": float(st.last_loss), "window_ms": nat_windows,
+              "what": "C++ mapper (csrc/mapper.cu, no torch, no Python in the loop): pinned keyframe image H2D on a copy stream "
+                      "(double-buffered), fused activations, forward, fused L1/D-SSIM loss, backward to compact gradients%s, one masked "
+                      "Adam launch that rebuilds dL/d(dc, sh) from dL/dcolour" % (
+                          ", colour-gradient push + 11-float two-shot reduce over NVLink peer memory" if world > 1 else "")}
+    mp.close()
+    del mp
+
+    # ---- e2e: the reference-facing LibTorch symbols driven by a C++ host (csrc/torch_host.cpp), host inputs every step -------
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    view_id = (rank * k) % 8
+    cam = cam0
+    params = [t(g["means"]).to(dev), t(g["dc"]).view(P, 1, 3).to(dev), t(g["sh"]).to(dev), t(g["opacity_logits"]).view(-1, 1).to(dev),
+              t(g["log_scales"]).to(dev), t(g["rots"]).to(dev)]                    # trainingSetup order (gaussian.cpp:399-424)
+    lrs = [1.6e-4, 2.5e-3, 2.5e-3 / 20.0, 0.05, 0.005, 0.001]                     # config/fastlivo.yaml:18-22
+    lims = [float(x) for x in cam["lims"]]
+    host = ops.shim().MappingHost(params, lrs, H, W, deg, cam["tanfovx"], cam["tanfovy"], lims, LAMBDA_DSSIM)
+    cam_host = torch.cat([t(cam["view"]), t(cam["proj"]), t(cam["campos"])]).pin_memory()
+    allreduce = None
+    if world > 1:
+        from gaussian_lic_b200 import dist as gdist
+        try:
+            allreduce = gdist.P2PGradAllReduce(P, M, dev)
+        except RuntimeError as e:                              # raised on every rank together: IPC not permitted here
+            print("[bench] %s -- NCCL all-reduce for the reference-shaped legs" % (e,), file=sys.stderr)
+            allreduce = gdist.GradAllReduce(P, M, dev)
+    _PACK = ("dL_dmeans3D", "dL_ddc", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drots")
+
+    def exchange(radii):
+        """mean of the per-view gradients + union of visibility through the packed exchange buffer"""
+        gr = host.grads()
+        for gi, n_ in zip(gr, _PACK):
+            allreduce.grads[n_].view_as(gi).copy_(gi)
+        _, vis8 = allreduce(radii)
+        for gi, n_ in zip(gr, _PACK):
+            gi.copy_(allreduce.grads[n_].view_as(gi))
+        return vis8.view(torch.bool)
 
     def e2e_step():
-        # per-iteration host inputs (gaussian.cpp:678): the 24.9 MB ground-truth image goes up on a copy stream and
-        # overlaps the forward; the camera block (140 B) is needed first and stays on the compute stream
-        with torch.cuda.stream(copy_stream):
-            gt_d = gt_host.to(dev, non_blocking=True)
-        cam_d = cam_host.to(dev, non_blocking=True)
-        rs = ops.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], lims[0], lims[1], lims[2], lims[3], bg, 1.0,
-                                               cam_d[:16].view(4, 4), cam_d[16:32].view(4, 4), deg, cam_d[32:35])
-        means2D = torch.zeros_like(params["means"], requires_grad=True)  # renderer.cpp:29
-        col, rad, _ = ops.GaussianRasterizer(rs)(params["means"], means2D, torch.sigmoid(params["op"]), params["dc"],
-                                                 params["sh"], torch.exp(params["log_s"]),
-                                                 torch.nn.functional.normalize(params["rot"]))
-        torch.cuda.current_stream(dev).wait_stream(copy_stream)
-        gt_d.record_stream(torch.cuda.current_stream(dev))
-        loss = (1.0 - LAMBDA_DSSIM) * ops.l1_loss(col, gt_d) + LAMBDA_DSSIM * (1.0 - ops.fused_ssim(col.unsqueeze(0), gt_d.unsqueeze(0)))
-        loss.backward()
-        for p_ in params.values():
-            p_.grad = None
-        return float(loss.item())                                        # D2H of the step's result
+        if world == 1:
+            return host.e2e_step(gt_host, cam_host)            # H2D image + camera, render, loss, backward, loss D2H: ONE C++ call
+        loss, radii = host.forward_backward(gt_host, cam_host)
+        exchange(radii)
+        val = float(loss.item())
+        host.optimizer_step(torch.zeros(P, dtype=torch.bool, device=dev))     # nothing visible: drops the gradients, moves nothing
+        return val
 
     for _ in range(3):
         e2e_step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
-    e2e = {"value": P * world / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4),
-           "h2d_bytes_per_step": int(gt_host.numel() * 4 + cam_host.numel() * 4), "d2h_bytes_per_step": 4 + 8,
-           "api": "RasterizeGaussiansCUDA/RasterizeGaussiansBackwardCUDA/fusedssim/fusedssim_backward (LibTorch shim) via autograd"}
+    e2e_ms, e2e_windows, _ = timed_windows(torch_window(e2e_step, steps), steps, world, dev, min_windows=3, min_total_ms=200.0)
+    e2e = {"value": P * world / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4), "window_ms": e2e_windows,
+           "h2d_bytes_per_step": int(gt_host.numel() * 4 + cam_host.numel() * 4), "d2h_bytes_per_step": 8,
+           "api": "RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / fusedssim / fusedssim_backward (LibTorch shim) under torch "
+                  "autograd, called from a C++ host (csrc/torch_host.cpp), one view per GPU%s" % (
+                      "; N > 1: + mean all-reduce of the six gradient tensors (own NVLink-P2P kernels)" if world > 1 else "")}
 
-    # ---- mapping iteration (BASELINE metric, second half): body of optimize()'s loop, gaussian.cpp:674-716 ----------
-    # H2D image, render, loss, backward, [all-reduce of the 6 gradient tensors over NCCL], visibility-masked Adam.
-    lrs = dict(means=1.6e-4, dc=2.5e-3, sh=2.5e-3 / 20.0, op=0.05, log_s=0.005, rot=0.001)      # config/fastlivo.yaml:18-22
-    opt = ops.SparseGaussianAdam([(params[k], lrs[k]) for k in ("means", "dc", "sh", "op", "log_s", "rot")])
-
-    _PACK = (("means", "dL_dmeans3D"), ("log_s", "dL_dscales"), ("rot", "dL_drots"), ("op", "dL_dopacity"),
-             ("dc", "dL_ddc"), ("sh", "dL_dsh"))
-
+    # ---- mapping iteration through the same symbols (BASELINE metric, second half; gaussian.cpp:674-716) ----------------------
     def mapping_iter():
-        with torch.cuda.stream(copy_stream):
-            gt_d = gt_host.to(dev, non_blocking=True)
-        cam_d = cam_host.to(dev, non_blocking=True)
-        rs = ops.GaussianRasterizationSettings(H, W, cam["tanfovx"], cam["tanfovy"], lims[0], lims[1], lims[2], lims[3], bg, 1.0,
-                                               cam_d[:16].view(4, 4), cam_d[16:32].view(4, 4), deg, cam_d[32:35])
-        means2D = torch.zeros_like(params["means"], requires_grad=True)
-        col, rad, _ = ops.GaussianRasterizer(rs)(params["means"], means2D, torch.sigmoid(params["op"]), params["dc"],
-                                                 params["sh"], torch.exp(params["log_s"]),
-                                                 torch.nn.functional.normalize(params["rot"]))
-        torch.cuda.current_stream(dev).wait_stream(copy_stream)
-        gt_d.record_stream(torch.cuda.current_stream(dev))
-        loss = (1.0 - LAMBDA_DSSIM) * ops.l1_loss(col, gt_d) + LAMBDA_DSSIM * (1.0 - ops.fused_ssim(col.unsqueeze(0), gt_d.unsqueeze(0)))
-        loss.backward()
-        visible = rad > 0
-        if world > 1 and args.exchange == "p2p":                         # mean of per-view gradients, union of visibility
-            for k_, n_ in _PACK:
-                allreduce.grads[n_].view_as(params[k_].grad).copy_(params[k_].grad)
-            _, vis8 = allreduce(rad)
-            for k_, n_ in _PACK:
-                params[k_].grad = allreduce.grads[n_].view_as(params[k_])
-            visible = vis8.view(torch.bool)
-        elif world > 1:
-            vis8 = visible.to(torch.uint8)
-            works = [dist.all_reduce(p_.grad, async_op=True) for p_ in params.values()]
-            works.append(dist.all_reduce(vis8, op=dist.ReduceOp.MAX, async_op=True))
-            for w_ in works:
-                w_.wait()
-            for p_ in params.values():
-                p_.grad.mul_(1.0 / world)
-            visible = vis8.bool()
-        opt.set_visibility_and_N(visible, P)
-        opt.step()
-        opt.zero_grad()
+        if world == 1:
+            return host.mapping_iter(gt_host, cam_host)
+        loss, radii = host.forward_backward(gt_host, cam_host)
+        host.optimizer_step(exchange(radii))
         return loss
 
     for _ in range(3):
         mapping_iter()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        mapping_iter()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    map_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
+    map_ms, _, _ = timed_windows(torch_window(mapping_iter, steps), steps, world, dev, min_windows=3, min_total_ms=200.0)
     mapping = {"ms_per_iter": round(map_ms, 4), "views_per_iter": world,
-               "what": "H2D image + render + L1/fused-SSIM loss + backward%s + SparseGaussianAdam (6 groups), LibTorch-shim symbols via autograd"
-                       % ((" + %s all-reduce of grads" % ("NVLink-P2P (own kernels)" if args.exchange == "p2p" else "NCCL")) if world > 1 else "")}
-
-    # ---- native mapping iteration (SURVEY 8f rank 1 + 3): packed model, C ABI only, one CUDA graph per rank ---------------
-    # pinned GT image H2D (double-buffered on the copy stream) -> [graph: activations, forward, fused loss, backward, chain
-    # rule, exchange, one-launch masked Adam].  Same work as `mapping_iter` without the torch autograd / optimizer plumbing.
-    native = None
-    try:
-        from gaussian_lic_b200 import model as gmodel
-        raw = dict(means=g["means"], log_scales=g["log_scales"], rots=g["rots"], opacity_logits=g["opacity_logits"],
-                   dc=g["dc"], sh=g["sh"], degree=deg)
-        mdl = gmodel.PackedModel(raw, dev, exchange=allreduce if (allreduce is not None and args.exchange == "p2p") else None)
-        gts = [torch.empty_like(gt), torch.empty_like(gt)]
-        graphs, done = [], [torch.cuda.Event(), torch.cuda.Event()]
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            r.stream = side.cuda_stream
-            gts[0].copy_(gt_host, non_blocking=True); gts[1].copy_(gt_host, non_blocking=True)
-            mdl.iteration(r, view, gts[0], color, T, radii, loss_out, dL)
-            side.synchronize()
-            for b in range(2):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
-                    r.stream = torch.cuda.current_stream(dev).cuda_stream
-                    mdl.iteration(r, view, gts[b], color, T, radii, loss_out, dL)
-                graphs.append(gr)
-        r.stream = None
-        torch.cuda.current_stream(dev).wait_stream(side)
-        it_no = [0]
-
-        def native_iter():
-            b = it_no[0] & 1
-            it_no[0] += 1
-            copy_stream.wait_event(done[b])                  # the graph that last read this buffer has finished
-            with torch.cuda.stream(copy_stream):
-                gts[b].copy_(gt_host, non_blocking=True)
-            torch.cuda.current_stream(dev).wait_stream(copy_stream)
-            graphs[b].replay()
-            done[b].record()
-
-        done[0].record(); done[1].record()
-        for _ in range(4):
-            native_iter()
-        torch.cuda.synchronize(dev)
-        assert not r.finish()
-        if world > 1:
-            dist.barrier()
-        e0.record()
-        for _ in range(args.steps):
-            native_iter()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        nat_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
-        assert not r.finish()
-        native = {"ms_per_iter": round(nat_ms, 4), "views_per_iter": world, "loss": float(loss_out.item()),
-                  "what": "pinned GT H2D (double-buffered) + ONE CUDA graph: fused activations, forward, fused L1/D-SSIM loss, backward, "
-                          "in-place chain rule%s, one-launch masked Adam on the packed model (C ABI only)"
-                          % (", NVLink-P2P exchange" if mdl.exchange is not None else "")}
-    except Exception as e:                                   # an extra metric must never cost the headline line
-        print("[bench] native mapping iteration unavailable: %r" % (e,), file=sys.stderr)
-        torch.cuda.synchronize(dev)
-
+               "what": "H2D image + render + L1/fused-SSIM loss + backward%s + adamUpdate x 6 groups: LibTorch-shim symbols, C++ host"
+                       % (" + mean all-reduce of the gradients" if world > 1 else "")}
     if rank != 0:
         return
-    cpu, _ = cpu_baseline(cfg, min(P, args.cpu_sample))
-    out = {"metric": METRIC, "value": value, "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps,
+    # ---- CPU legs (rank 0): the oracle port, median of 3; the forward-only cfg1 figure BASELINE configs[0] names ---------------
+    cpus = [cpu_baseline(cfg, min(P, args.cpu_sample))[0] for _ in range(3)]
+    cpu = sorted(cpus, key=lambda c: c["value"])[1]
+    cpu["sample"] += "; median of 3 runs (%s)" % ", ".join("%.0f" % c["value"] for c in cpus)
+    cpu["cfg1_forward_only"] = cpu_forward_cfg1()
+    extra_sort = None
+    if world == 1 and not args.no_sort_bench:
+        try:
+            extra_sort = sort_microbench(torch)
+        except Exception as e:                                # an extra metric must never cost the headline line
+            print("[bench] sort microbench skipped: %r" % (e,), file=sys.stderr)
+    out = {"metric": METRIC, "value": value, "unit": "Gaussians/s", "n_gpus": world, "steps": steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
-           "timing": {"how": "median of %d device-timed windows of exactly %d steps (barrier + sync both sides, max over ranks per window)"
-                             % (len(windows), args.steps), "window_ms_per_step": windows, "per_rank_ms_per_step": per_rank},
+           "timing": {"how": "median of %d device-timed windows of exactly %d steps (barrier + sync both sides, CUDA events on the "
+                             "launching stream, max over ranks per window)" % (len(windows), steps),
+                      "window_ms_per_step": windows, "per_rank_ms_per_step": per_rank},
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s: %d Gaussians, %dx%d, SH degree %d, forward + fused L1/D-SSIM loss + backward, "
-                                  "1 view per GPU" % (cfg, P, W, H, deg),
-                      "P": P, "V": V, "R": Rn, "B": Bn, "views_per_gpu": 1,
-                      "parallelism": "dp%d (view-sharded%s)" % (world, (", in-place all-reduce of packed grads: %s" % ("own NVLink-P2P kernels" if args.exchange == "p2p" else "NCCL")) if world > 1 else ""),
-                      "l2": "per-step working set ~%.1f GB > 126 MB L2 (no explicit flush)" % (A1 / 1e9),
-                      "cuda_graph": graph is not None},
-           "clocks": clocks, "e2e": e2e, "mapping_iter": mapping, "mapping_iter_native": native, "gpu_launches": int(launches), "roofline": roofline,
-           "cpu_baseline": cpu}
-    print(json.dumps(out))
+           "config": {"workload": "%s: %d Gaussians, %dx%d, SH degree %d, forward + fused L1/D-SSIM loss + backward, %d view%s per GPU"
+                                  % (cfg, P, W, H, deg, k, "" if k == 1 else "s"),
+                      "P": P, "V": V, "R": Rn, "B": Bn, "views_per_gpu": k,
+                      "parallelism": "dp%d (view-sharded%s)" % (world, ", exchange = NVLink push of per-view colour gradients + two-shot "
+                                                                "mean-reduce of 11 geometric floats per Gaussian (own kernels / copy engines)" if world > 1 else ""),
+                      "host": "C++ mapper (csrc/mapper.cu), plain launches on one stream, no host synchronisation inside the window",
+                      "l2": "per-step working set ~%.1f GB > 126 MB L2 (no explicit flush)" % (A1 * k / 1e9),
+                      "binning_overflow_regrows": int(regrows)},
+           "clocks": clocks, "e2e": e2e, "mapping_iter": mapping, "mapping_iter_native": native, "gpu_launches": int(launches),
+           "roofline": roofline, "cpu_baseline": cpu}
+    if extra_sort is not None:
+        out["sort_cfg5"] = extra_sort
+    emit((out))
+
+
+def run_loop(args):
+    """BASELINE configs[3] (cfg4): the full mapping loop -- per keyframe extend() (alpha-only render, LiDAR z-buffer
+    de-duplication, in-place append) then optimize() (view sampler, 100 iterations of render + loss + backward + [exchange] +
+    Adam) -- on the native mapper, 1 vs N GPUs.  mapping.cpp has no prune step (gaussian.cpp has none either); "densify" is
+    extend().  With N GPUs an iteration consumes N sampled views, so a keyframe's 100 view-renders take ceil(100/N) steps."""
+    import torch
+    from gaussian_lic_b200 import mapper as gmapper, synthetic as syn
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+    cfg = args.config
+    P, W, H, fx, fy, cx, cy, deg, zmax = syn.CONFIGS[cfg]
+    K, n_lidar = args.keyframes, args.lidar_points
+    g, _ = syn.make_scene(cfg)
+    # a map under construction: the right-hand ~30 % of view 0's field of view has no Gaussians yet, so extend() has room to insert
+    keep = g["means"][:, 0] < 0.4 * np.abs(g["means"][:, 2]) * W / (2 * fx)
+    g = {kk: (v[keep] if isinstance(v, np.ndarray) and v.shape[:1] == keep.shape else v) for kk, v in g.items()}
+    P = int(keep.sum())
+    gts = [torch.as_tensor(syn.make_gt_image(W, H, seed=7 + i)).pin_memory() for i in range(min(K, 4))]
+    mp = gmapper.Mapper(W, H, fx, fy, cx, cy, sh_degree=deg, capacity=P + K * n_lidar, max_iters=100, seed=1, rank=rank, world=world,
+                        views_per_rank=1)
+    mp.initialize(g)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, mp.export_handle())
+        mp.connect(handles)
+        dist.barrier()
+    rng = np.random.default_rng(5)
+    ext_ms, opt_ms, inserted, iters = [], [], [], 0
+    torch.cuda.synchronize(dev)
+    t_wall = time.perf_counter()
+    for kf in range(K):
+        R_wc, t_wc = syn.orbit_pose(kf % 8, radius=args.rig_radius)
+        mp.add_keyframe(R_wc, t_wc, gts[kf % len(gts)])
+        z = rng.uniform(0.5, zmax, n_lidar)                                    # one LiDAR sweep inside this camera's frustum
+        pc = np.stack([z * rng.uniform(-1.0, 1.0, n_lidar) * W / (2 * fx), z * rng.uniform(-1.0, 1.0, n_lidar) * H / (2 * fy), z], 1)
+        pts = (pc @ np.asarray(R_wc).T + np.asarray(t_wc)).astype(np.float32)
+        cols = rng.uniform(0, 1, (n_lidar, 3)).astype(np.float32)
+        inserted.append(int(mp.extend(pts, cols, z.astype(np.float32))))
+        st = mp.stats()
+        ext_ms.append(float(st.ms_extend))
+        st = mp.optimize()
+        opt_ms.append(float(st.ms_optimize))
+        iters = int(st.iterations)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t_wall
+    tot_opt = max_over_ranks(float(np.sum(opt_ms)), world)
+    tot_ext = max_over_ranks(float(np.sum(ext_ms)), world)
+    psnr, ssim = mp.evaluate(K - 1)
+    st = mp.stats()
+    mp.close()
+    if rank != 0:
+        return
+    views = sum(min(i + 1, 100) for i in range(K))
+    emit(({
+        "metric": "mapping-iter ms (full loop)", "value": round(tot_opt / max(iters, 1), 4), "unit": "ms/iteration", "n_gpus": world,
+        "higher_is_better": False, "scaling": "strong", "dtype": "f32", "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": "%s recipe: %d initial Gaussians (right-hand 30 %% of the view left empty), %dx%d, SH degree %d, %d keyframes x (extend %d LiDAR points + optimize <= 100 views)"
+                               % (cfg, P, W, H, deg, K, n_lidar), "views_per_iteration": world},
+        "iterations": iters, "view_renders": views, "ms_per_view_render": round(tot_opt / max(views, 1), 4), "optimize_ms_total": round(tot_opt, 2),
+        "extend_ms_total": round(tot_ext, 2), "extend_ms_mean": round(tot_ext / K, 3), "inserted_per_keyframe": inserted,
+        "final_gaussians": int(st.num_gaussians), "capacity": int(st.capacity), "overflow_regrows": int(st.overflow_regrows),
+        "last_keyframe_psnr": round(psnr, 3), "last_keyframe_ssim": round(ssim, 4), "last_loss": float(st.last_loss),
+        "wall_s_including_host_scene_generation": round(wall, 2)}))
+
+
+def cpu_forward_cfg1():
+    """BASELINE configs[0]: 10 k Gaussians, 640x480, SH degree 0, forward only, on the host cores (the reference has no CPU
+    path: this is the oracle port), 1 thread and all physical cores."""
+    from oracle.oracle import Oracle
+    syn = load_synthetic()
+    o = Oracle(np.float32)
+    g, cam = syn.make_scene("cfg1")
+    res = {}
+    for label, n in (("1_thread", 1), ("all_cores", physical_cores())):
+        o.set_threads(n)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            f = o.forward(g, cam)
+            ts.append(time.perf_counter() - t0)
+            o.free(f)
+        res[label] = {"threads": n, "ms": round(1e3 * float(np.median(ts)), 2), "Gaussians_per_s": round(10_000 / float(np.median(ts)), 1)}
+    return res
 
 
 def run_reference(args):
@@ -567,7 +619,7 @@ def run_reference(args):
         base.update({"value": cpu["value"], "ms_per_step": round(cpu_dt * 1e3 * P / min(P, args.cpu_sample), 2),
                      "reference_kind": "cpu oracle port (oracle/_ref not built or no GPU)",
                      "e2e": {"value": cpu["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base))
+        emit((base))
         return
     import torch
     spec = importlib.util.spec_from_file_location("glic_ref_ext", so)
@@ -651,7 +703,14 @@ def run_reference(args):
                                   "what": "reference loop body: H2D image + render + loss + backward + reference SparseGaussianAdam"},
                  "e2e": {"value": P / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4),
                          "h2d_bytes_per_step": int(gt_host.numel() * 4 + cam_host.numel() * 4), "d2h_bytes_per_step": 4}})
-    print(json.dumps(base))
+    if not args.no_sort_bench and hasattr(ref, "cub_sort_pairs"):
+        try:
+            del params
+            torch.cuda.empty_cache()
+            base["sort_cfg5"] = sort_microbench(torch, ref=ref)
+        except Exception as e:
+            print("[bench] sort microbench skipped: %r" % (e,), file=sys.stderr)
+    emit((base))
 
 
 def main():
@@ -664,13 +723,19 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="Gaussians in the bounded CPU-baseline sample")
     ap.add_argument("--view", type=int, default=None, help="view of the 8-view rig to render (default: rank % 8)")
     ap.add_argument("--rig-radius", type=float, default=0.25, help="radius [m] of the multi-view rig")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1 gradient exchange: own NVLink peer-memory all-reduce (default) or the NCCL library call")
-    ap.add_argument("--no-graph", action="store_true", help="do not CUDA-graph the resident-input step")
+    ap.add_argument("--views-per-gpu", type=int, default=1, help="views each GPU renders per iteration (gradient accumulation)")
+    ap.add_argument("--loop", action="store_true", help="run the full mapping loop (extend + optimize per keyframe) on --config; default for cfg4")
+    ap.add_argument("--keyframes", type=int, default=10, help="--loop: keyframes (each: extend + up to 100 optimisation views)")
+    ap.add_argument("--lidar-points", type=int, default=20000, help="--loop: LiDAR points offered to extend() per keyframe")
+    ap.add_argument("--no-sort-bench", action="store_true", help="skip the cfg5 sort microbenchmark appended to the N = 1 line")
+    ap.add_argument("--no-graph", action="store_true", help="(kept for old command lines; the mapper launches plainly)")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (for ncu captures; not a bench value)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.loop or args.config == "cfg4":
+        run_loop(args)
     else:
         run_ours(args)
 

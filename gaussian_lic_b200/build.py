@@ -69,7 +69,7 @@ TORCH_LIB = os.path.join(PKG, TORCH_NAME + ".so")
 def build_torch_shim(verbose=False, force=False):
     """LibTorch shim (reference operator symbols + pybind face) linked against libglic_b200.so."""
     build_cuda(verbose=False)
-    srcs = [os.path.join(CSRC, "torch_shim.cpp"), os.path.join(CSRC, "torch_shim_py.cpp")]
+    srcs = [os.path.join(CSRC, "torch_shim.cpp"), os.path.join(CSRC, "torch_shim_py.cpp"), os.path.join(CSRC, "torch_host.cpp")]
     if not force and not _newer(TORCH_LIB, srcs + _headers()):
         return TORCH_LIB
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")

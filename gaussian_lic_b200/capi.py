@@ -118,6 +118,7 @@ def _load():
         "glic_mapper_export": (i32, [vp, C.c_char_p]),
         "glic_mapper_connect": (i32, [vp, C.c_char_p]),
         "glic_mapper_synchronize": (i32, [vp]),
+        "glic_mapper_set_option": (i32, [vp, i32, i32]),
         "glic_debug_geom": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "glic_debug_binning": (i32, [i32, vp, i64, i64, vp, vp, vp, vp]),
         "glic_debug_image": (i32, [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp]),

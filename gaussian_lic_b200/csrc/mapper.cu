@@ -116,7 +116,7 @@ struct glic_mapper {
     uint64_t view_counter = 0;
     glic_mapper_stats st{};
     double vis_sum = 0; uint64_t vis_iters = 0;
-    std::vector<void*> graveyard;         // buffers replaced by a regrow; freed at the next synchronisation point
+    bool run_optimizer = true;            // GLIC_MAPPER_OPT_OPTIMIZER (benchmarks time the rasterization step alone with it off)
 };
 
 namespace {
@@ -262,7 +262,7 @@ int iteration(glic_mapper* m, const int* views) {
         const int buf = (int)(m->view_counter++ & 1);
         // keyframe image H2D on the copy stream (gaussian.cpp:678), overlapping the previous view's backward / Adam
         GLIC_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->gt_free[buf], 0));
-        GLIC_CUDA_TRY(cudaMemcpyAsync(m->gt_dev[buf], kf.image, sizeof(float) * 3 * (size_t)W * H, cudaMemcpyHostToDevice, m->copy_stream));
+        GLIC_CUDA_TRY(cudaMemcpyAsync(m->gt_dev[buf], kf.image, sizeof(float) * 3 * (size_t)W * H, cudaMemcpyDefault, m->copy_stream));
         GLIC_CUDA_TRY(cudaEventRecord(m->gt_ready[buf], m->copy_stream));
         MAP_TRY(forward_view(m, kf, 0, j == m->k - 1 ? m->counters_host + 4 * r : nullptr));
         uint8_t* fl = flag_slot(m, parity, slot);
@@ -310,6 +310,7 @@ int iteration(glic_mapper* m, const int* views) {
     const float color_scale = m->M ? 1.0f / (float)m->S : 0.0f;
     float campos[MAX_SLOTS * 4];
     for (int sl = 0; sl < m->S; ++sl) std::memcpy(campos + 4 * sl, m->train[views[sl]].cam.campos, 16);
+    if (m->run_optimizer)
     MAP_TRY(launch_adam_compact(m->P, m->Pcap, m->D, m->M, m->params, m->m1, m->m2, geo, m->Pcap, lr6, col_slot(m, parity, 0), flag_slot(m, parity, 0),
                                 campos, m->S, 1.0f / (float)m->k, color_scale, 0.9f, 0.999f, 1e-15f, reinterpret_cast<const unsigned int*>(geo_tail), m->vis_acc, s));
     GLIC_CUDA_TRY(cudaMemcpyAsync(m->loss_host + r, m->loss_dev + 1, sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -603,6 +604,14 @@ int glic_mapper_stats_get(glic_mapper* m, glic_mapper_stats* out) {
     if (!m || !out) { set_error("mapper_stats: null pointer"); return GLIC_ERR_INVALID_ARGUMENT; }
     *out = m->st;
     return GLIC_OK;
+}
+
+int glic_mapper_set_option(glic_mapper* m, int option, int value) {
+    if (!m) { set_error("mapper_set_option: null mapper"); return GLIC_ERR_INVALID_ARGUMENT; }
+    switch (option) {
+        case GLIC_MAPPER_OPT_OPTIMIZER: m->run_optimizer = value != 0; return GLIC_OK;
+        default: set_error("mapper_set_option: unknown option"); return GLIC_ERR_INVALID_ARGUMENT;
+    }
 }
 
 int glic_mapper_synchronize(glic_mapper* m) {

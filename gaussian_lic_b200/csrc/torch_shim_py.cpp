@@ -37,7 +37,10 @@ torch::Tensor fusedssim_backward(float C1, float C2, torch::Tensor& img1, torch:
 
 torch::Tensor distCUDA2(const torch::Tensor& points);
 
+void glic_bind_host(pybind11::module_& m);   // torch_host.cpp: C++ host of the mapping-iteration body on these symbols
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    glic_bind_host(m);
     m.def("RasterizeGaussiansCUDA", &RasterizeGaussiansCUDA);
     m.def("RasterizeGaussiansBackwardCUDA", &RasterizeGaussiansBackwardCUDA);
     m.def("adamUpdate", &adamUpdate);

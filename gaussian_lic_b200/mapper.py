@@ -113,6 +113,9 @@ class Mapper:
         capi.check(capi.lib.glic_mapper_stats_get(self._h, C.byref(st)), "mapper_stats")
         return st
 
+    def set_optimizer(self, on):
+        capi.check(capi.lib.glic_mapper_set_option(self._h, 1, int(bool(on))), "mapper_set_option")
+
     def synchronize(self):
         capi.check(capi.lib.glic_mapper_synchronize(self._h), "mapper_synchronize")
 

@@ -389,6 +389,11 @@ GLIC_API int glic_mapper_download(glic_mapper* m, float* xyz, float* f_dc, float
 GLIC_API int glic_mapper_export(glic_mapper* m, unsigned char* handle64);
 GLIC_API int glic_mapper_connect(glic_mapper* m, const unsigned char* handles /* [world][64] */);
 GLIC_API int glic_mapper_synchronize(glic_mapper* m);
+/* options: GLIC_MAPPER_OPT_OPTIMIZER (default 1): 0 leaves the Adam launch out of the iteration, so that a benchmark can time
+ * the rasterization step (activations, forward, loss, backward, exchange) on its own.  Keyframe images may be device pointers
+ * (the copy uses cudaMemcpyDefault): that is how "inputs resident in HBM" is measured. */
+enum { GLIC_MAPPER_OPT_OPTIMIZER = 1 };
+GLIC_API int glic_mapper_set_option(glic_mapper* m, int option, int value);
 /* Camera (camera.h:38-110) in closed form, as the mapper derives it from a keyframe pose: out41 = view[16] (column-major
  * Rt) | proj[16] (column-major P*Rt) | campos[3] | tan_fovx, tan_fovy | limx_neg, limx_pos, limy_neg, limy_pos. */
 GLIC_API int glic_camera_block(int width, int height, float fx, float fy, float cx, float cy, const float* R_wc /*[9] row-major*/,
