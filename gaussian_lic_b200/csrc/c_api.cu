@@ -154,7 +154,7 @@ int glic_forward_preprocess(int P, int sh_degree, int M, const float* means3D, c
     GLIC_CUDA_TRY(cudaEventRecord(r_event, r_stream));
     {   // depth-first binning: order the Gaussians by (depth, index) once, then prefix-sum their tile counts in that order
         StageTimer _t(GLIC_STAGE_SORT, s);
-        const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
+        const int cur = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s, nullptr, /*hist_ready=*/true);
         if (cur < 0) return cur;
         if (int e = launch_depth_scan(P, g, g.order[cur], 0xFFFFFFFFll, s)) return e;
     }
@@ -190,10 +190,12 @@ int glic_forward_render(int P, const glic_view* view, int no_color, int64_t R, v
 
     int cur = 0;
     if (R > 0) {
-        { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], R, s)) return e; }
         const int bit = (int)higher_msb((uint32_t)T);                       // rasterizer_impl.cu:417
+        { StageTimer _t(GLIC_STAGE_EMIT, s);
+          if (int e = sort_prepare(R, bit, bin.sort_temp, s)) return e;      // emit builds the tile sort's digit histograms
+          if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], R, sort_hist(bin.sort_temp), bit, s)) return e; }
         // pairs arrive ordered by (depth, index): a stable sort on the tile bits alone finishes the job
-        { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs32(R, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s); }
+        { StageTimer _t(GLIC_STAGE_SORT, s); cur = launch_sort_pairs32(R, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s, nullptr, true); }
         if (cur < 0) return cur;
     }
     GLIC_CUDA_TRY(cudaMemsetAsync(&bin.hdr->sorted_in_b, cur, 1, s));       // 0/1 in the low byte (header is zero-padded)
@@ -257,14 +259,16 @@ int glic_forward(int P, int sh_degree, int M, const float* means3D, const float*
       if (int e = launch_preprocess_forward(P, sh_degree, M, means3D, scales, scale_modifier, rotations, opacities, dc, sh, vp,
                                             no_color != 0, radii, g, s)) return e; }
     { StageTimer _t(GLIC_STAGE_SORT, s);
-      const int cur0 = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s);
+      const int cur0 = launch_sort_pairs32(P, 32, g.depth_keys, g.order, g.sort_temp, g.sort_temp_size, s, nullptr, /*hist_ready=*/true);
       if (cur0 < 0) return cur0;
       if (int e = launch_depth_scan(P, g, g.order[cur0], cap, s)) return e; }
-    { StageTimer _t(GLIC_STAGE_EMIT, s); if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], cap, s)) return e; }
+    const int bit = (int)higher_msb((uint32_t)T);
+    { StageTimer _t(GLIC_STAGE_EMIT, s);
+      if (int e = sort_prepare(cap, bit, bin.sort_temp, s)) return e;        // emit builds the tile sort's digit histograms
+      if (int e = launch_emit_keys(P, vp, g, bin.keys[0], bin.vals[0], cap, sort_hist(bin.sort_temp), bit, s)) return e; }
     int cur;
     { StageTimer _t(GLIC_STAGE_SORT, s);
-      const int bit = (int)higher_msb((uint32_t)T);
-      cur = launch_sort_pairs32(cap, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s, &g.hdr->r_eff);
+      cur = launch_sort_pairs32(cap, bit, bin.keys, bin.vals, bin.sort_temp, bin.sort_temp_size, s, &g.hdr->r_eff, true);
       if (cur < 0) return cur; }
     GLIC_CUDA_TRY(cudaMemsetAsync(&bin.hdr->sorted_in_b, cur, 1, s));       // 0/1 in the low byte (header is zero-padded)
     GLIC_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char*>(&bin.hdr->sorted_in_b) + 1, 0, 3, s));

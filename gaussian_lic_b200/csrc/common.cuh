@@ -252,13 +252,18 @@ int launch_preprocess_forward(int P, int D, int M, const float* means, const flo
                               const float* rots, const float* opac, const float* dc, const float* sh,
                               const ViewParams& vp, bool no_color, int* radii, GeomState g, cudaStream_t s);
 int launch_depth_scan(int P, GeomState g, const uint32_t* order, int64_t capacity, cudaStream_t s);
-int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, cudaStream_t s);
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, uint32_t* sort_hist_out,
+                     int end_bit, cudaStream_t s);
 // Sorts on bits [0,end_bit); returns 0/1 = index of the ping-pong buffer holding the result, <0 on error.
 int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
                       cudaStream_t s);
 // n_dev (optional): device-side true count <= n; kernels are launched for n (a capacity) and clip to *n_dev.
 int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                        cudaStream_t s, const unsigned int* n_dev = nullptr);
+                        cudaStream_t s, const unsigned int* n_dev = nullptr, bool hist_ready = false);
+// A producer kernel may build the digit histograms itself: sort_prepare() zeroes the temp block, the producer adds one count
+// per key and pass into sort_hist(temp)[pass * 256 + digit], and the sort is launched with hist_ready = true.
+int sort_prepare(int64_t n, int end_bit, void* temp, cudaStream_t s);
+uint32_t* sort_hist(void* temp);
 // R: host-side count or capacity; r_dev (optional): device-side true count
 int launch_tile_ranges(int64_t R, const GeomHeader* ghdr, const uint32_t* tile_keys_sorted, int T, ImageState img, bool buckets,
                        cudaStream_t s);

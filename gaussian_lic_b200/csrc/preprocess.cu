@@ -148,7 +148,12 @@ GLIC_DI void row_span(float cox, float coy, float coz, float mx, float my, float
 template <bool EMIT>
 GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float cox, float coy, float coz, float thr, int x0,
                                  int y0, int rw, int grid_x, uint32_t idx, uint32_t off, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+                                 uint32_t* __restrict__ vals, uint32_t* s_hist = nullptr, uint32_t hi_mask = 0) {
+    // EMIT: every key written also counts into the CTA's two digit histograms of the tile sort (bits [0,8) and [8,..))
+    auto count_key = [&](uint32_t key) {
+        atomicAdd(&s_hist[key & 255u], 1u);
+        if (hi_mask) atomicAdd(&s_hist[256 + ((key >> 8) & hi_mask)], 1u);
+    };
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool big = n > WALK_SMALL;
@@ -178,7 +183,7 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
         const int x1 = x0 + rw;
         for (int t = 0; t < n; ++t) {
             if (tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr) {
-                if (EMIT) { keys[off + count] = (uint32_t)(ty * grid_x + tx); vals[off + count] = idx; }
+                if (EMIT) { const uint32_t key = (uint32_t)(ty * grid_x + tx); keys[off + count] = key; vals[off + count] = idx; count_key(key); }
                 ++count;
             }
             if (++tx == x1) { tx = x0; ++ty; }
@@ -247,7 +252,7 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
                 uint32_t pos = w.off[s] + basev + (incl - cnt);
                 const uint32_t gi = w.idx[s];
                 const uint32_t t0 = (uint32_t)(ty * grid_x);
-                for (int x = xa; x <= xb; ++x, ++pos) { keys[pos] = t0 + (uint32_t)x; vals[pos] = gi; }
+                for (int x = xa; x <= xb; ++x, ++pos) { keys[pos] = t0 + (uint32_t)x; vals[pos] = gi; count_key(t0 + (uint32_t)x); }
             }
         }
     }
@@ -260,9 +265,11 @@ __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, const float* __restrict__ scales,
                           float mod, const float4* __restrict__ rots, const float* __restrict__ opac,
                           const float* __restrict__ dc, const float* __restrict__ sh, ViewParams vp, bool no_color,
-                          int* __restrict__ radii, GeomState g) {
+                          int* __restrict__ radii, GeomState g, uint32_t* __restrict__ depth_hist) {
     __shared__ float s_view[16], s_proj[16], s_cam[3];
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
+    __shared__ uint32_t s_dhist[4 * 256];                   // digit histograms of the depth keys (the P-sized sort's four passes)
+    for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) s_dhist[i] = 0;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float (*s_sh)[32 * SH_ROW_MAX] = reinterpret_cast<float (*)[32 * SH_ROW_MAX]>(dyn_smem);   // one 32-row SH slab per warp
     WalkSmem& walk = *reinterpret_cast<WalkSmem*>(dyn_smem + sizeof(float) * (PRE_THREADS / 32) * 32 * SH_ROW_MAX);
@@ -427,8 +434,16 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         g.rec[3 * idx + 2] = make_float4(blue, depth, __int_as_float(radius), hy);
         g.clamped[idx] = (uint8_t)clampbits;
         g.tiles[idx] = tiles;
-        g.depth_keys[0][idx] = tiles ? __float_as_uint(depth) : 0xFFFFFFFFu;   // culled Gaussians sort to the end
+        const uint32_t dkey = tiles ? __float_as_uint(depth) : 0xFFFFFFFFu;   // culled Gaussians sort to the end
+        g.depth_keys[0][idx] = dkey;
         g.order[0][idx] = (uint32_t)idx;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) atomicAdd(&s_dhist[p * 256 + ((dkey >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * 256; i += PRE_THREADS) {
+        const uint32_t v = s_dhist[i];
+        if (v) atomicAdd(&depth_hist[i], v);
     }
 }
 
@@ -438,6 +453,8 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
 // Prefix sum of tiles_touched over the DEPTH order (single-pass decoupled look-back; the per-CTA work is a
 // few loads, so no CTA ever delays its successors): Gaussian order[pos] owns slots [end - tiles, end) and
 // `end` is scattered to offsets[gaussian] so that the emit kernel can run in (well mixed) index order.
+constexpr int SCAN_ITEMS = 4;
+
 __global__ void __launch_bounds__(PRE_THREADS)
 depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsigned int capacity) {
     __shared__ unsigned s_block;
@@ -447,10 +464,18 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsign
     if (tid == 0) s_block = atomicAdd(&g.hdr->ticket, 1u);
     __syncthreads();
     const int block = (int)s_block;
-    const int pos = block * PRE_THREADS + tid;
-    uint32_t gid = 0, tiles = 0;
-    if (pos < P) { gid = order[pos]; tiles = g.tiles[gid]; }
-    uint32_t incl = tiles;
+    const int pos0 = (block * PRE_THREADS + tid) * SCAN_ITEMS;
+    uint32_t gid[SCAN_ITEMS], run[SCAN_ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; ++e) {
+        gid[e] = 0;
+        uint32_t tiles = 0;
+        if (pos0 + e < P) { gid[e] = order[pos0 + e]; tiles = g.tiles[gid[e]]; }
+        mine += tiles;
+        run[e] = mine;                                       // inclusive within the thread
+    }
+    uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -480,14 +505,21 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsign
         }
     }
     __syncthreads();
-    if (pos < P) g.offsets[gid] = s_block_excl + s_warp_sum[warp] + incl;
+    const uint32_t base = s_block_excl + s_warp_sum[warp] + incl - mine;
+#pragma unroll
+    for (int e = 0; e < SCAN_ITEMS; ++e)
+        if (pos0 + e < P) g.offsets[gid[e]] = base + run[e];
 }
 
 // Key emission in index order: Gaussian idx re-walks its rect with the same exact test and writes
 // key = tile id, value = idx into its slot range [offsets[idx] - tiles, offsets[idx]).
 __global__ void __launch_bounds__(PRE_THREADS)
-emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned int capacity) {
+emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned int capacity,
+                 uint32_t* __restrict__ sort_hist, uint32_t hi_mask) {
     __shared__ WalkSmem walk;
+    __shared__ uint32_t s_hist[2 * 256];
+    for (int i = threadIdx.x; i < 2 * 256; i += PRE_THREADS) s_hist[i] = 0;
+    __syncthreads();
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     int n = 0, x0 = 0, y0 = 0, rw = 1;
     float mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, thr = 0.f;
@@ -509,7 +541,12 @@ emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys,
             n = (rc.y1 - rc.y0) * rw;
         }
     }
-    block_tile_walk<true>(walk, skip ? 0 : n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals);
+    block_tile_walk<true>(walk, skip ? 0 : n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals, s_hist, hi_mask);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 256; i += PRE_THREADS) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&sort_hist[i], v);
+    }
 }
 
 int launch_preprocess_forward(int P, int D, int M, const float* means, const float* scales, float mod,
@@ -519,6 +556,7 @@ int launch_preprocess_forward(int P, int D, int M, const float* means, const flo
     // header (ticket/total) and the emit kernel's look-back status words start at zero
     GLIC_CUDA_TRY(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
     GLIC_CUDA_TRY(cudaMemsetAsync(g.scan_status, 0, sizeof(unsigned long long) * (blocks + 1), s));
+    if (int e = sort_prepare(P, 32, g.sort_temp, s)) return e;       // the depth sort's histograms are built by this kernel
     const size_t dyn = sizeof(float) * (PRE_THREADS / 32) * 32 * SH_ROW_MAX + sizeof(WalkSmem);
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set)) {
@@ -526,21 +564,26 @@ int launch_preprocess_forward(int P, int D, int M, const float* means, const flo
     }
     preprocess_forward_kernel<<<blocks, PRE_THREADS, dyn, s>>>(P, D, M, means, scales, mod,
                                                              reinterpret_cast<const float4*>(rots), opac, dc, sh, vp,
-                                                             no_color, radii, g);
+                                                             no_color, radii, g, sort_hist(g.sort_temp));
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }
 
 int launch_depth_scan(int P, GeomState g, const uint32_t* order, int64_t capacity, cudaStream_t s) {
     const unsigned int cap = (unsigned int)std::min<int64_t>(capacity, 0xFFFFFFFFll);
-    depth_scan_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, g, order, cap);
+    const int per_cta = PRE_THREADS * SCAN_ITEMS;
+    depth_scan_kernel<<<(P + per_cta - 1) / per_cta, PRE_THREADS, 0, s>>>(P, g, order, cap);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }
 
-int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, cudaStream_t s) {
+// sort_hist_out: the [passes][256] digit histograms of the following tile sort (zeroed by sort_prepare); end_bit = its key bits
+int launch_emit_keys(int P, const ViewParams& vp, GeomState g, uint32_t* tile_keys, uint32_t* vals, int64_t capacity, uint32_t* sort_hist_out,
+                     int end_bit, cudaStream_t s) {
     const unsigned int cap = (unsigned int)std::min<int64_t>(capacity, 0xFFFFFFFFll);
-    emit_keys_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, vp, g, tile_keys, vals, cap);
+    if (end_bit > 16) { set_error("emit_keys: more than 16 tile bits"); return GLIC_ERR_INVALID_ARGUMENT; }
+    const uint32_t hi_mask = end_bit > 8 ? (1u << (end_bit - 8)) - 1u : 0u;
+    emit_keys_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(P, vp, g, tile_keys, vals, cap, sort_hist_out, hi_mask);
     GLIC_LAUNCH_CHECK();
     return GLIC_OK;
 }

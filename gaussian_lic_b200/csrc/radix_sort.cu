@@ -18,14 +18,17 @@
 
 namespace glic {
 
+int sort_prepare(int64_t n, int end_bit, void* temp, cudaStream_t s);
+
 namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per CTA
+constexpr int SORT_ITEMS_BIG = 16;                     // 4096 pairs per CTA: the R-sized tile sort
+constexpr int SORT_ITEMS_SMALL = 4;                    // 1024 pairs per CTA: inputs that would not fill the GPU with 4096-pair tiles
+constexpr int64_t SORT_SMALL_LIMIT = (int64_t)148 * 4 * SORT_THREADS * SORT_ITEMS_BIG;     // below ~2.4 M pairs use the small tile
 constexpr int MAX_PASSES = 8;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -38,7 +41,8 @@ struct SortTemp {
     uint32_t* status;   // [passes][blocks][RADIX]
 };
 
-__host__ inline int64_t sort_blocks(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+__host__ inline int sort_items(int64_t n) { return n < SORT_SMALL_LIMIT ? SORT_ITEMS_SMALL : SORT_ITEMS_BIG; }
+__host__ inline int64_t sort_blocks(int64_t n) { const int64_t tile = (int64_t)SORT_THREADS * sort_items(n); return (n + tile - 1) / tile; }
 
 __host__ inline SortTemp carve_sort_temp(void* temp) {
     char* p = static_cast<char*>(temp);
@@ -104,8 +108,9 @@ __global__ void __launch_bounds__(RADIX) sort_scan_hist_kernel(uint32_t* __restr
 }
 
 // ---- 3. one onesweep pass -------------------------------------------------------------------
-template <typename KeyT>
+template <typename KeyT, int SORT_ITEMS>
 struct __align__(16) PassSmem {
+    static constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     KeyT keys[SORT_TILE];
     uint32_t vals[SORT_TILE];
     uint32_t warp_cnt[SORT_WARPS][RADIX];
@@ -115,14 +120,15 @@ struct __align__(16) PassSmem {
     uint32_t block_id;
 };
 
-template <typename KeyT>
-__global__ void __launch_bounds__(SORT_THREADS, sizeof(KeyT) == 4 ? 5 : 3)
+template <typename KeyT, int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS <= 4 ? 6 : (sizeof(KeyT) == 4 ? 5 : 3))
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, const unsigned int* __restrict__ n_dev,
                      int shift, int bits, const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status,
                      uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PassSmem<KeyT>& sm = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+    PassSmem<KeyT, SORT_ITEMS>& sm = *reinterpret_cast<PassSmem<KeyT, SORT_ITEMS>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t dmask = (1u << bits) - 1u;
 
@@ -256,40 +262,35 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
 
 }  // namespace
 
+// zeroes the histograms, tickets and look-back status words of a sort of n pairs on bits [0, end_bit)
+int sort_prepare(int64_t n, int end_bit, void* temp, cudaStream_t s) {
+    if (n <= 0) return GLIC_OK;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const size_t used = sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)passes * sort_blocks(n) * RADIX);
+    GLIC_CUDA_TRY(cudaMemsetAsync(temp, 0, used, s));
+    return GLIC_OK;
+}
+
+uint32_t* sort_hist(void* temp) { return static_cast<uint32_t*>(temp); }      // [MAX_PASSES][256], pass-major
+
 size_t sort_temp_bytes(int64_t n) {
     const size_t blocks = (size_t)sort_blocks(n > 0 ? n : 1);
     return sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)MAX_PASSES * blocks * RADIX) + 256;
 }
 
-template <typename KeyT>
-static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                               cudaStream_t s, const unsigned int* n_dev = nullptr) {
-    if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
-    if (n >= (int64_t)VALUE_MASK) { set_error("sort: n too large"); return GLIC_ERR_INVALID_ARGUMENT; }
-    if (n <= 0) return 0;
-    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    if (passes > MAX_PASSES) { set_error("sort: too many passes"); return GLIC_ERR_INVALID_ARGUMENT; }
-    if (temp_bytes < sort_temp_bytes(n)) { set_error("sort: temp too small"); return GLIC_ERR_WORKSPACE; }
-    const int64_t blocks = sort_blocks(n);
-    SortTemp t = carve_sort_temp(temp);
-    const size_t used = sizeof(uint32_t) * (MAX_PASSES * RADIX + 32 + (size_t)passes * blocks * RADIX);
-    GLIC_CUDA_TRY(cudaMemsetAsync(temp, 0, used, s));
-
+template <typename KeyT, int ITEMS>
+static int run_passes(int64_t n, int passes, int end_bit, int64_t blocks, KeyT* keys[2], uint32_t* vals[2], const SortTemp& t, cudaStream_t s,
+                      const unsigned int* n_dev) {
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set)) {
-        GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(PassSmem<KeyT>)));
+        GLIC_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PassSmem<KeyT, ITEMS>)));
     }
-    int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
-    sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, n_dev, passes, end_bit, t.hist);
-    GLIC_LAUNCH_CHECK();
-    sort_scan_hist_kernel<<<passes, RADIX, 0, s>>>(t.hist);
-    GLIC_LAUNCH_CHECK();
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * RADIX_BITS;
         const int bits = min(RADIX_BITS, end_bit - shift);
-        onesweep_pass_kernel<KeyT><<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem<KeyT>), s>>>(
+        onesweep_pass_kernel<KeyT, ITEMS><<<(unsigned)blocks, SORT_THREADS, sizeof(PassSmem<KeyT, ITEMS>), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev, shift, bits, t.hist + p * RADIX,
             t.status + (size_t)p * blocks * RADIX, t.tickets + p);
         GLIC_LAUNCH_CHECK();
@@ -298,14 +299,39 @@ static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* 
     return cur;
 }
 
+// hist_ready: the caller zeroed the temp block with sort_prepare() and a producer kernel already accumulated the digit
+// histograms of every pass into sort_hist(temp) (sort_hist_add): the histogram kernel -- one more read of all keys -- is skipped.
+template <typename KeyT>
+static int launch_sort_pairs_t(int64_t n, int end_bit, KeyT* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
+                               cudaStream_t s, const unsigned int* n_dev = nullptr, bool hist_ready = false) {
+    if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort: end_bit out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (n >= (int64_t)VALUE_MASK) { set_error("sort: n too large"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (n <= 0) return 0;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (passes > MAX_PASSES) { set_error("sort: too many passes"); return GLIC_ERR_INVALID_ARGUMENT; }
+    if (temp_bytes < sort_temp_bytes(n)) { set_error("sort: temp too small"); return GLIC_ERR_WORKSPACE; }
+    const int64_t blocks = sort_blocks(n);
+    SortTemp t = carve_sort_temp(temp);
+    if (!hist_ready) {
+        if (int e = sort_prepare(n, end_bit, temp, s)) return e;
+        int hist_blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)148 * 8);
+        sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys[0], n, n_dev, passes, end_bit, t.hist);
+        GLIC_LAUNCH_CHECK();
+    }
+    sort_scan_hist_kernel<<<passes, RADIX, 0, s>>>(t.hist);
+    GLIC_LAUNCH_CHECK();
+    return sort_items(n) == SORT_ITEMS_SMALL ? run_passes<KeyT, SORT_ITEMS_SMALL>(n, passes, end_bit, blocks, keys, vals, t, s, n_dev)
+                                             : run_passes<KeyT, SORT_ITEMS_BIG>(n, passes, end_bit, blocks, keys, vals, t, s, n_dev);
+}
+
 int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
                       cudaStream_t s) {
     return launch_sort_pairs_t<uint64_t>(n, end_bit, keys, vals, temp, temp_bytes, s);
 }
 
 int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* vals[2], void* temp, size_t temp_bytes,
-                        cudaStream_t s, const unsigned int* n_dev) {
-    return launch_sort_pairs_t<uint32_t>(n, end_bit, keys, vals, temp, temp_bytes, s, n_dev);
+                        cudaStream_t s, const unsigned int* n_dev, bool hist_ready) {
+    return launch_sort_pairs_t<uint32_t>(n, end_bit, keys, vals, temp, temp_bytes, s, n_dev, hist_ready);
 }
 
 }  // namespace glic
