@@ -80,7 +80,8 @@ struct GeomHeader {
     unsigned int order_cur;     // which ping-pong half holds the depth-sorted order
     unsigned int r_eff;         // R when it fits the binning workspace, else 0: what the sort / ranges / render use
     unsigned int overflow;      // 1 when R exceeded the capacity (frame invalid, caller re-runs with more room)
-    unsigned int pad[26];
+    unsigned int span_count;    // bump allocator of the row-span arena (preprocess -> emit)
+    unsigned int pad[25];
 };
 
 size_t sort_temp_bytes(int64_t n);
@@ -92,6 +93,9 @@ struct GeomState {
     uint32_t* order[2];         // Gaussian indices, sorted by (depth, index) after the depth sort
     uint32_t* tiles;            // tiles_touched per Gaussian (index order)
     uint32_t* offsets;          // per Gaussian: END of its slot range = inclusive scan of tiles over the depth order
+    uint32_t* tmask;            // per Gaussian: accept mask of a <= 32-tile rect, or first row-span entry of a bigger one
+    uint32_t* spans;            // row spans (xa | xb << 16) of the big rects, bump-allocated per frame
+    uint32_t span_cap;
     uint8_t* clamped;
     unsigned long long* scan_status;
     void* sort_temp;
@@ -108,6 +112,9 @@ struct GeomState {
         g.order[1] = c.take<uint32_t>(n);
         g.tiles = c.take<uint32_t>(n);
         g.offsets = c.take<uint32_t>(n);
+        g.tmask = c.take<uint32_t>(n);
+        g.span_cap = (uint32_t)(4 * n);
+        g.spans = c.take<uint32_t>(4 * n);
         g.clamped = c.take<uint8_t>(n);
         g.scan_status = c.take<unsigned long long>((n + PRE_THREADS - 1) / PRE_THREADS + 1);
         g.sort_temp_size = sort_temp_bytes((int64_t)n);

@@ -1,7 +1,4 @@
-// extend.cu -- EXPERIMENTAL (written at the end of round 1 with the GPU budget spent: compiled, not yet executed on a GPU;
-// its parity test, tests/test_gpu_extend.py, runs only with GLIC_EXPERIMENTAL=1).
-//
-// GPU form of extend() (/root/reference/src/gaussian.cpp:499-638): which LiDAR points of the newest
+// extend.cu -- GPU form of extend() (/root/reference/src/gaussian.cpp:499-638): which LiDAR points of the newest
 // frame become Gaussians and with which initial parameters.  The reference projects on the GPU, copies every pixel
 // coordinate to the host, de-duplicates through an unordered_map<std::string, ...> and copies the survivors back.
 // Here: one 64-bit atomicMin per in-image point on a (orderable depth bits << 32 | index) word per pixel -- the
@@ -136,7 +133,7 @@ size_t glic_extend_bytes(int n, int width, int height) {
     return pix + flags + 256;
 }
 
-// EXPERIMENTAL, see the file header.  All pointers are device pointers except R_cw_host[9] (row-major) / t_cw_host[3] and
+// All pointers are device pointers except R_cw_host[9] (row-major) / t_cw_host[3] and
 // count_host (pinned or pageable; valid after the stream is synchronised by this call).  Output arrays have room for n rows.
 int glic_extend(int n, const float* points, const float* colors, const float* depth_rsp, const float* R_cw_host,
                 const float* t_cw_host, float fx, float fy, float cx, float cy, int width, int height, const float* final_T,

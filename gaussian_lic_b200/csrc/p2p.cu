@@ -132,9 +132,9 @@ void launch_reduce(const PeerBufs& pb, size_t lo4, size_t hi4, size_t vis_off, s
     p2p_reduce_kernel<WORLD, UNROLL><<<blocks, 512, 0, s>>>(pb, lo4, hi4, vis_off, vlo4, vhi4, 1.0f / (float)WORLD);
 }
 
-// ---- EXPERIMENTAL: reduce-scatter -> Adam on the local slice -> all-gather of PARAMETERS ------------------
-// Written at the end of round 1, compiled but not yet executed (opt-in test tests/test_gpu_p2p_adam.py).  Same NVLink
-// bytes as the all-reduce (gradients in, parameters out), Adam's HBM traffic and its moment buffers divided by `world`.
+// ---- reduce-scatter -> Adam on the local slice -> all-gather of PARAMETERS ---------------------------------
+// Same NVLink bytes as the all-reduce (gradients in, parameters out), Adam's HBM traffic and its moment buffers divided by
+// `world`; bit-identical to all-reduce + packed Adam (tests/test_gpu_p2p_adam.py).
 struct P2PLayout {
     size_t begin[6], end[6];
     uint32_t k[6];
@@ -278,7 +278,7 @@ size_t glic_p2p_model_bytes(size_t n_floats, size_t n_vis_bytes) {
     return glic_p2p_buffer_bytes(n_floats, n_vis_bytes) + ((n_floats * 4 + 255) & ~size_t(255));
 }
 
-// EXPERIMENTAL (see above).  bufs_host[q]: rank q's glic_p2p_model_bytes block.  exp_avg / exp_avg_sq: LOCAL, 16-byte aligned,
+// bufs_host[q]: rank q's glic_p2p_model_bytes block.  exp_avg / exp_avg_sq: LOCAL, 16-byte aligned,
 // n_floats rounded up to a multiple of 4 floats each (only this rank's slice is ever touched).  After the call every rank's parameter block holds the updated model.
 int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P, uint32_t M, float* exp_avg, float* exp_avg_sq,
                          const float* lr6_host, float b1, float b2, float eps, void* stream) {

@@ -10,9 +10,10 @@
 //     pairs on the 13 tile bits only (2 passes, 32-bit keys).  A stable sort by tile of a sequence ordered
 //     by (depth, index) is ordered by (tile, depth, index): the final list is bit-identical to the
 //     reference's, at ~1/4 of the sort traffic;
-//   * the emit kernel fuses the prefix sum of tiles_touched (over the depth order) by single-pass decoupled
-//     look-back over dynamically ordered CTAs -- no scan kernel, no scan temp;
-//   * tile counting and key emission walk all (Gaussian, tile) pairs of a warp in a balanced flat list;
+//   * the prefix sum of tiles_touched over the depth order is a single-pass decoupled look-back scan;
+//   * the exact tile test runs ONCE per candidate tile: the counting walk stores each Gaussian's accept set (32-bit mask
+//     or per-row spans), the emitting walk only expands it; both walks are balanced across the CTA;
+//   * the digit histograms of both radix sorts are accumulated by the kernels that produce the keys;
 //   * one 48-byte AoS splat record per Gaussian feeds emit, render-forward and render-backward;
 //   * every key-defining operation uses the fixed-order intrinsics of geom_math.cuh.
 #include "geom_math.cuh"
@@ -88,6 +89,17 @@ GLIC_DI uint32_t lookback_exclusive(unsigned long long* status, int block, uint3
 // range is arbitrary for big rects -- the tile ids of one Gaussian are distinct, so the sorted list does
 // not depend on it.
 constexpr int WALK_SMALL = 32;
+constexpr uint32_t NO_SPANS = 0xFFFFFFFFu;
+
+// What the counting walk (preprocess) leaves behind for the emitting walk, so that no exact tile test runs twice:
+//   rects of <= 32 tiles: the accept set as a 32-bit mask (bit t <-> t-th tile of the rect, row-major) in tmask[i];
+//   bigger rects: one (xa | xb << 16) word per rect row in a bump-allocated arena, first entry in tmask[i]
+//   (NO_SPANS when the arena is full: the emitting walk then recomputes that rect's rows with the exact test).
+struct SpanStore {
+    uint32_t* spans;
+    uint32_t cap;
+    unsigned int* counter;
+};
 
 struct WalkSmem {
     uint32_t row_prefix[PRE_THREADS + 1];     // exclusive prefix of row counts over the compacted big list
@@ -95,6 +107,7 @@ struct WalkSmem {
     float mx[PRE_THREADS], my[PRE_THREADS], cox[PRE_THREADS], coy[PRE_THREADS], coz[PRE_THREADS], thr[PRE_THREADS];
     int x0[PRE_THREADS], y0[PRE_THREADS], rw[PRE_THREADS], n[PRE_THREADS];
     uint32_t off[PRE_THREADS], idx[PRE_THREADS];
+    uint32_t base[PRE_THREADS];               // first entry of the rect's row spans in the span arena (NO_SPANS: none)
     uint32_t warp_big[PRE_THREADS / 32];
     uint32_t n_big, n_rows;
 };
@@ -148,7 +161,8 @@ GLIC_DI void row_span(float cox, float coy, float coz, float mx, float my, float
 template <bool EMIT>
 GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float cox, float coy, float coz, float thr, int x0,
                                  int y0, int rw, int grid_x, uint32_t idx, uint32_t off, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals, uint32_t* s_hist = nullptr, uint32_t hi_mask = 0) {
+                                 uint32_t* __restrict__ vals, SpanStore ss, uint32_t& mask_or_base, uint32_t* s_hist = nullptr,
+                                 uint32_t hi_mask = 0) {
     // EMIT: every key written also counts into the CTA's two digit histograms of the tile sort (bits [0,8) and [8,..))
     auto count_key = [&](uint32_t key) {
         atomicAdd(&s_hist[key & 255u], 1u);
@@ -175,19 +189,29 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
         w.x0[slot] = x0; w.y0[slot] = y0; w.rw[slot] = rw; w.n[slot] = n;
         w.off[slot] = off; w.idx[slot] = idx;
         w.cursor[slot] = 0;
+        if (!EMIT) {                                     // room for this rect's row spans
+            const uint32_t rows = (uint32_t)(n / rw);
+            const uint32_t b = atomicAdd(ss.counter, rows);
+            mask_or_base = (b + rows <= ss.cap) ? b : NO_SPANS;
+        }
+        w.base[slot] = mask_or_base;
     }
     // -- small rects: own lane, row-major, every tile tested
     uint32_t count = 0;
     if (n > 0 && !big) {
         int tx = x0, ty = y0;
         const int x1 = x0 + rw;
+        uint32_t mask = EMIT ? mask_or_base : 0u;
         for (int t = 0; t < n; ++t) {
-            if (tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr) {
+            const bool in = EMIT ? ((mask >> t) & 1u) != 0 : tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr;
+            if (in) {
                 if (EMIT) { const uint32_t key = (uint32_t)(ty * grid_x + tx); keys[off + count] = key; vals[off + count] = idx; count_key(key); }
+                else mask |= 1u << t;
                 ++count;
             }
             if (++tx == x1) { tx = x0; ++ty; }
         }
+        if (!EMIT) mask_or_base = mask;
     }
     __syncthreads();
     if (total_big == 0) return count;
@@ -225,8 +249,16 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
         }
         int xa = 1, xb = 0, ty = 0;
         if (valid) {
-            ty = w.y0[s] + (int)(item - w.row_prefix[s]);
-            row_span(w.cox[s], w.coy[s], w.coz[s], w.mx[s], w.my[s], w.thr[s], ty, w.x0[s], w.x0[s] + w.rw[s], xa, xb);
+            const uint32_t row = item - w.row_prefix[s];
+            ty = w.y0[s] + (int)row;
+            const uint32_t sb = w.base[s];
+            if (EMIT && sb != NO_SPANS) {
+                const uint32_t sp = ss.spans[sb + row];
+                xa = (int)(sp & 0xFFFFu); xb = (int)(sp >> 16);
+            } else {
+                row_span(w.cox[s], w.coy[s], w.coz[s], w.mx[s], w.my[s], w.thr[s], ty, w.x0[s], w.x0[s] + w.rw[s], xa, xb);
+                if (!EMIT && sb != NO_SPANS) ss.spans[sb + row] = xb >= xa ? ((uint32_t)xa | ((uint32_t)xb << 16)) : 1u;   // (1, 0) = empty
+            }
         }
         const uint32_t cnt = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
         // rows of one Gaussian sit in consecutive lanes: segmented (by slot) inclusive scan, one atomic per segment
@@ -248,11 +280,33 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
             const uint32_t ahead = lastmask & ~((1u << lane) - 1u);          // segment ends at or after this lane
             const int src = ahead ? (__ffs(ahead) - 1) : lane;
             const uint32_t basev = __shfl_sync(FULL, seg_base, src);
-            if (cnt) {
-                uint32_t pos = w.off[s] + basev + (incl - cnt);
-                const uint32_t gi = w.idx[s];
-                const uint32_t t0 = (uint32_t)(ty * grid_x);
-                for (int x = xa; x <= xb; ++x, ++pos) { keys[pos] = t0 + (uint32_t)x; vals[pos] = gi; count_key(t0 + (uint32_t)x); }
+            // The 32 rows of this step hold `tot` pairs.  They are written FLAT: lane l takes pairs l, l + 32, ... of the step and
+            // finds its row with a 5-step search over the rows' inclusive counts, so that one store instruction covers up to
+            // 32 consecutive slots of a row (rows of one Gaussian are adjacent in memory too) instead of 32 different rows.
+            const uint32_t row_pos = cnt ? w.off[s] + basev + (incl - cnt) : 0u;     // first slot of this lane's row
+            const uint32_t row_key = (uint32_t)(ty * grid_x + xa);
+            const uint32_t row_gid = valid ? w.idx[s] : 0u;
+            uint32_t fin = cnt;                                                       // inclusive count over the step's rows
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, fin, o);
+                if (lane >= o) fin += t;
+            }
+            const uint32_t tot = __shfl_sync(FULL, fin, 31);
+            for (uint32_t e = lane; e < ((tot + 31u) & ~31u); e += 32) {
+                // row r = first lane whose inclusive count exceeds e
+                int r = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    const uint32_t probe = __shfl_sync(FULL, fin, r + st - 1);
+                    if (probe <= e) r += st;
+                }
+                const uint32_t r_fin = __shfl_sync(FULL, fin, r), r_cnt = __shfl_sync(FULL, cnt, r);
+                const uint32_t r_pos = __shfl_sync(FULL, row_pos, r), r_key = __shfl_sync(FULL, row_key, r), r_gid = __shfl_sync(FULL, row_gid, r);
+                if (e < tot) {
+                    const uint32_t j = e - (r_fin - r_cnt);                           // position inside the row
+                    keys[r_pos + j] = r_key + j; vals[r_pos + j] = r_gid; count_key(r_key + j);
+                }
             }
         }
     }
@@ -347,7 +401,9 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         }
     }
     // ---- phase 2: exact tile counting, balanced across the CTA --------------------------------------------
-    const uint32_t cnt = block_tile_walk<false>(walk, n, mx, my, cox, coy, coz, thr, rx0, ry0, rw, vp.grid_x, 0u, 0u, nullptr, nullptr);
+    uint32_t mask_or_base = 0;
+    const SpanStore ss{g.spans, g.span_cap, &g.hdr->span_count};
+    const uint32_t cnt = block_tile_walk<false>(walk, n, mx, my, cox, coy, coz, thr, rx0, ry0, rw, vp.grid_x, 0u, 0u, nullptr, nullptr, ss, mask_or_base);
     // ---- phase 3: colour of the survivors -----------------------------------------------------------------
     if (sh_tma) mbar_wait(&s_bar, 0);      // (the walk's __syncthreads order thread 0's barrier init before every wait)
     if (cnt > 0) {
@@ -434,6 +490,7 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
         g.rec[3 * idx + 2] = make_float4(blue, depth, __int_as_float(radius), hy);
         g.clamped[idx] = (uint8_t)clampbits;
         g.tiles[idx] = tiles;
+        g.tmask[idx] = mask_or_base;
         const uint32_t dkey = tiles ? __float_as_uint(depth) : 0xFFFFFFFFu;   // culled Gaussians sort to the end
         g.depth_keys[0][idx] = dkey;
         g.order[0][idx] = (uint32_t)idx;
@@ -448,8 +505,6 @@ preprocess_forward_kernel(int P, int D, int M, const float* __restrict__ means, 
 }
 
 // ---- key emission ----------------------------------------------------------------------------
-// One thread per Gaussian re-walks its rect with the same exact test and writes
-// key = (tile << 32) | bits(depth), value = Gaussian index into its [offsets[i-1], offsets[i]) slots.
 // Prefix sum of tiles_touched over the DEPTH order (single-pass decoupled look-back; the per-CTA work is a
 // few loads, so no CTA ever delays its successors): Gaussian order[pos] owns slots [end - tiles, end) and
 // `end` is scattered to offsets[gaussian] so that the emit kernel can run in (well mixed) index order.
@@ -511,8 +566,9 @@ depth_scan_kernel(int P, GeomState g, const uint32_t* __restrict__ order, unsign
         if (pos0 + e < P) g.offsets[gid[e]] = base + run[e];
 }
 
-// Key emission in index order: Gaussian idx re-walks its rect with the same exact test and writes
-// key = tile id, value = idx into its slot range [offsets[idx] - tiles, offsets[idx]).
+// Key emission in index order: Gaussian idx expands the accept set the counting walk stored (tile mask / row spans; the
+// exact test is only re-run for rects whose spans did not fit the arena) and writes key = tile id, value = idx into its
+// slot range [offsets[idx] - tiles, offsets[idx]); the tile sort's digit histograms are counted on the way.
 __global__ void __launch_bounds__(PRE_THREADS)
 emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned int capacity,
                  uint32_t* __restrict__ sort_hist, uint32_t hi_mask) {
@@ -523,11 +579,12 @@ emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys,
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     int n = 0, x0 = 0, y0 = 0, rw = 1;
     float mx = 0.f, my = 0.f, cox = 0.f, coy = 0.f, coz = 0.f, thr = 0.f;
-    uint32_t off = 0;
+    uint32_t off = 0, mask_or_base = 0;
     bool skip = false;
     if (idx < P) {
         const uint32_t tiles = g.tiles[idx];
         if (tiles != 0) {
+            mask_or_base = g.tmask[idx];
             const float4 r0 = g.rec[3 * (size_t)idx + 0];
             const float4 r1 = g.rec[3 * (size_t)idx + 1];
             const float4 r2 = g.rec[3 * (size_t)idx + 2];
@@ -541,7 +598,9 @@ emit_keys_kernel(int P, ViewParams vp, GeomState g, uint32_t* __restrict__ keys,
             n = (rc.y1 - rc.y0) * rw;
         }
     }
-    block_tile_walk<true>(walk, skip ? 0 : n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals, s_hist, hi_mask);
+    const SpanStore ss{g.spans, g.span_cap, &g.hdr->span_count};
+    block_tile_walk<true>(walk, skip ? 0 : n, mx, my, cox, coy, coz, thr, x0, y0, rw, vp.grid_x, (uint32_t)idx, off, keys, vals, ss, mask_or_base,
+                          s_hist, hi_mask);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * 256; i += PRE_THREADS) {
         const uint32_t v = s_hist[i];

@@ -173,8 +173,7 @@ class P2PGradAllReduce:
 
 
 class P2PModelExchange(P2PGradAllReduce):
-    """EXPERIMENTAL (never run on a GPU yet; opt-in test tests/test_gpu_p2p_adam.py): the fused form of the exchange.
-    The mapped block additionally holds the PARAMETERS (packed layout); `step(radii)` reduce-scatters the gradients,
+    """The fused form of the exchange on full packed gradients (tests/test_gpu_p2p_adam.py).  The mapped block additionally holds the PARAMETERS (packed layout); `step(radii)` reduce-scatters the gradients,
     applies the visibility-masked Adam to this rank's slice only and all-gathers the updated parameters into every
     replica (csrc/p2p.cu, glic_p2p_reduce_adam).  The moment buffers are touched on the local slice only."""
 

