@@ -725,7 +725,7 @@ def main():
     ap.add_argument("--rig-radius", type=float, default=0.25, help="radius [m] of the multi-view rig")
     ap.add_argument("--views-per-gpu", type=int, default=1, help="views each GPU renders per iteration (gradient accumulation)")
     ap.add_argument("--loop", action="store_true", help="run the full mapping loop (extend + optimize per keyframe) on --config; default for cfg4")
-    ap.add_argument("--keyframes", type=int, default=10, help="--loop: keyframes (each: extend + up to 100 optimisation views)")
+    ap.add_argument("--keyframes", type=int, default=45, help="--loop: keyframes (each: extend + one optimisation pass over the keyframes so far, <= 100 views): 45 keyframes = 1035 view renders")
     ap.add_argument("--lidar-points", type=int, default=20000, help="--loop: LiDAR points offered to extend() per keyframe")
     ap.add_argument("--no-sort-bench", action="store_true", help="skip the cfg5 sort microbenchmark appended to the N = 1 line")
     ap.add_argument("--no-graph", action="store_true", help="(kept for old command lines; the mapper launches plainly)")
