@@ -269,7 +269,7 @@ int launch_sort_pairs32(int64_t n, int end_bit, uint32_t* keys[2], uint32_t* val
                         cudaStream_t s, const unsigned int* n_dev = nullptr, bool hist_ready = false);
 // A producer kernel may build the digit histograms itself: sort_prepare() zeroes the temp block, the producer adds one count
 // per key and pass into sort_hist(temp)[pass * 256 + digit], and the sort is launched with hist_ready = true.
-int sort_prepare(int64_t n, int end_bit, void* temp, cudaStream_t s);
+int sort_prepare(int64_t n, int end_bit, void* temp, cudaStream_t s, int digit_bits = 8);
 uint32_t* sort_hist(void* temp);
 // R: host-side count or capacity; r_dev (optional): device-side true count
 int launch_tile_ranges(int64_t R, const GeomHeader* ghdr, const uint32_t* tile_keys_sorted, int T, ImageState img, bool buckets,

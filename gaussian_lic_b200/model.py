@@ -106,15 +106,28 @@ class PackedModel:
 
     # ---- one mapping iteration (asynchronous; CUDA-graph capturable) -------------------------------------------
     def iteration(self, rast, view, gt, color, final_T, radii, loss_out, dL_dpix, lambda_dssim=0.2):
-        s = rast.stream
-        self.activate(s)
-        rast.forward(self.inputs, view, out_color=color, out_T=final_T, radii=radii, sync=False)
-        rast.loss(color, gt, lambda_dssim, loss_out, dL_dpix)
-        rast.backward(self.inputs, view, radii, dL_dpix, self.packed.grads)
-        self.chain_rule(s)
-        if self.exchange is not None:
-            _, visible = self.exchange(radii)
-        else:
-            visible = self.packed.visible
-            torch.gt(radii[:self.P], 0, out=visible.view(torch.bool))
-        self.adam(visible, s)
+        """One iteration on ONE stream: rast.stream when set, else torch's current stream (the C-ABI launches, the visibility
+        mask and the exchange must not straddle two streams).  A binning-capacity overflow of an EARLIER iteration (the frame
+        rendered empty and Adam stepped on stale momentum) is reported here, with a lag, from the pinned counters: the caller
+        regrows (`rast.finish()`) and re-captures its graph.  The native mapper (csrc/mapper.cu) handles this on the device."""
+        if int(rast.counters[2]) != 0:
+            raise capi.GlicError("binning capacity overflow in an earlier iteration (true R = %d > capacity %d): call rast.finish(), "
+                                 "re-capture and redo the step" % (int(rast.counters[0]), rast.cap))
+        handle = rast.stream if rast.stream else torch.cuda.current_stream(self.device).cuda_stream
+        keep, rast.stream = rast.stream, handle
+        try:
+            with torch.cuda.stream(torch.cuda.ExternalStream(handle, device=self.device)):
+                s = C.c_void_p(handle)
+                self.activate(s)
+                rast.forward(self.inputs, view, out_color=color, out_T=final_T, radii=radii, sync=False)
+                rast.loss(color, gt, lambda_dssim, loss_out, dL_dpix)
+                rast.backward(self.inputs, view, radii, dL_dpix, self.packed.grads)
+                self.chain_rule(s)
+                if self.exchange is not None:
+                    _, visible = self.exchange(radii)
+                else:
+                    visible = self.packed.visible
+                    torch.gt(radii[:self.P], 0, out=visible.view(torch.bool))
+                self.adam(visible, s)
+        finally:
+            rast.stream = keep
