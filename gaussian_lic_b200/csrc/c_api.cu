@@ -338,9 +338,16 @@ int glic_backward_compact_internal(int P, int sh_degree, int M, const float* mea
     GeomState g = GeomState::carve(const_cast<void*>(geom_ws), P);
     ImageState img = ImageState::carve(const_cast<void*>(image_ws), vp.W, vp.H);
     { StageTimer _t(GLIC_STAGE_ZERO, s);
-    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, s));
-    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 4 * (size_t)P, s));
-    GLIC_CUDA_TRY(cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)P, s));
+    // conic | mean2D | opacity carved from ONE block (the mapper's capacity layout): one memset over the span when the slack
+    // between the live prefixes is small, three otherwise
+    const ptrdiff_t span = dL_dconic < dL_dmeans2D && dL_dmeans2D < dL_dopacity ? (dL_dopacity + P) - dL_dconic : -1;
+    if (span > 0 && span <= 10 * (ptrdiff_t)P) {
+        GLIC_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * (size_t)span, s));
+    } else {
+        GLIC_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, s));
+        GLIC_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 4 * (size_t)P, s));
+        GLIC_CUDA_TRY(cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)P, s));
+    }
     GLIC_CUDA_TRY(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, s)); }
     if (R > 0) {
         BinningState bin = BinningState::carve(const_cast<void*>(binning_ws), R);

@@ -170,14 +170,15 @@ int set_capacity(glic_mapper* m, uint32_t cap) {
         MAP_TRY(glic_arena_regrow(m->m2, m->Pcap, n2, cap, (uint32_t)m->M, m->P, m->stream));
         GLIC_CUDA_TRY(cudaStreamSynchronize(m->stream));
     }
-    void* old[] = {m->params, m->m1, m->m2, m->act_opacity, m->act_scales, m->act_rots, m->radii, m->g_mean2D, m->g_conic, m->g_opacity,
-                   m->geom_ws, m->xblock};
+    void* old[] = {m->params, m->m1, m->m2, m->act_opacity, m->act_scales, m->act_rots, m->radii, m->g_conic, m->geom_ws, m->xblock};
     for (void* p : old) if (p) cudaFree(p);
     m->params = np; m->m1 = n1; m->m2 = n2;
     MAP_TRY(dev_alloc((void**)&m->act_opacity, (size_t)cap * 4)); MAP_TRY(dev_alloc((void**)&m->act_scales, (size_t)cap * 12));
     MAP_TRY(dev_alloc((void**)&m->act_rots, (size_t)cap * 16)); MAP_TRY(dev_alloc((void**)&m->radii, (size_t)cap * 4));
-    MAP_TRY(dev_alloc((void**)&m->g_mean2D, (size_t)cap * 12)); MAP_TRY(dev_alloc((void**)&m->g_conic, (size_t)cap * 16));
-    MAP_TRY(dev_alloc((void**)&m->g_opacity, (size_t)cap * 4));
+    // the three 2-D gradient accumulators the render backward adds into: one block (conic first: float4-aligned)
+    MAP_TRY(dev_alloc((void**)&m->g_conic, (size_t)cap * (16 + 12 + 4)));
+    m->g_mean2D = m->g_conic + (size_t)cap * 4;
+    m->g_opacity = m->g_mean2D + (size_t)cap * 3;
     m->geom_bytes = glic_geom_bytes((int)cap);
     MAP_TRY(dev_alloc(&m->geom_ws, m->geom_bytes));
     m->xbytes = xblock_layout(m, cap);
@@ -378,7 +379,7 @@ int glic_mapper_destroy(glic_mapper* m) {
     if (!m) return GLIC_OK;
     cudaDeviceSynchronize();
     for (void* p : m->opened) cudaIpcCloseMemHandle(p);
-    void* bufs[] = {m->params, m->m1, m->m2, m->act_opacity, m->act_scales, m->act_rots, m->radii, m->g_mean2D, m->g_conic, m->g_opacity, m->geom_ws,
+    void* bufs[] = {m->params, m->m1, m->m2, m->act_opacity, m->act_scales, m->act_rots, m->radii, m->g_conic, m->geom_ws,
                     m->xblock, m->image_ws, m->binning_ws, m->sample_ws, m->loss_scratch, m->eval_scratch, m->extend_ws, m->color, m->final_T, m->dL_dpix,
                     m->gt_dev[0], m->gt_dev[1], m->loss_dev, m->eval_out, m->vis_acc};
     for (void* p : bufs) if (p) cudaFree(p);

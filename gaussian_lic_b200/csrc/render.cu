@@ -61,20 +61,23 @@ tile_ranges_kernel(int64_t R, const unsigned int* __restrict__ r_dev, const uint
     }
 }
 
-// bucket_offsets = inclusive scan of ceil(n_t / 32); single CTA (T is a few thousand).
-__global__ void __launch_bounds__(1024)
-bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ bucket_offsets, ImageHeader* hdr,
-                   long long R, const GeomHeader* __restrict__ ghdr, int buckets) {
+// Inclusive scan over the T tiles by ONE CTA of 1024 threads, 8 consecutive tiles per thread (8192 tiles per sweep: one sweep
+// covers a 1080p frame): thread-serial scan of its 8 values, warp scan, scan of the 32 warp totals -- two barriers per sweep.
+template <typename Load, typename Store>
+__device__ __forceinline__ uint32_t cta_scan_tiles(int T, Load load, Store store) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
+    constexpr int PER = 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        uint32_t v = 0;
-        if (t < T && buckets) { const uint2 r = ranges[t]; v = (r.y - r.x + BUCKET - 1) / BUCKET; }
-        uint32_t incl = v;
+    for (int base = 0; base < T; base += 1024 * PER) {
+        const int t0 = base + tid * PER;
+        uint32_t v[PER];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) { v[e] = t0 + e < T ? load(t0 + e) : 0u; mine += v[e]; v[e] = mine; }
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -82,27 +85,39 @@ bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict
         }
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_tot[lane], wi = w;
+        uint32_t wbase = 0;
+        {
+            const uint32_t w = warp_tot[lane];
+            uint32_t wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += n;
             }
-            warp_tot[lane] = wi - w;
+            wbase = __shfl_sync(0xffffffffu, wi - w, warp);            // exclusive total of the warps before mine
         }
+        const uint32_t before = carry + wbase + incl - mine;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) if (t0 + e < T) store(t0 + e, before + v[e]);
         __syncthreads();
-        const uint32_t out = carry + warp_tot[warp] + incl;
-        if (t < T) bucket_offsets[t] = out;
-        __syncthreads();
-        if (tid == 1023) carry = out;
+        if (tid == 1023) carry = before + mine;
         __syncthreads();
     }
-    if (tid == 0) {
+    return carry;
+}
+
+// bucket_offsets = inclusive scan of ceil(n_t / 32)
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ bucket_offsets, ImageHeader* hdr,
+                   long long R, const GeomHeader* __restrict__ ghdr, int buckets) {
+    const uint32_t total = cta_scan_tiles(
+        T, [&](int t) { if (!buckets) return 0u; const uint2 r = ranges[t]; return (r.y - r.x + BUCKET - 1) / BUCKET; },
+        [&](int t, uint32_t v) { bucket_offsets[t] = v; });
+    if (threadIdx.x == 0) {
         long long true_R = R, ovf = 0;
         if (ghdr) { R = ghdr->r_eff; true_R = ghdr->total; ovf = ghdr->overflow; }
-        hdr->num_buckets = carry; hdr->num_rendered = R;
-        hdr->counters[0] = true_R; hdr->counters[1] = carry; hdr->counters[2] = ovf; hdr->counters[3] = 0;
+        hdr->num_buckets = total; hdr->num_rendered = R;
+        hdr->counters[0] = true_R; hdr->counters[1] = total; hdr->counters[2] = ovf; hdr->counters[3] = 0;
     }
 }
 
@@ -283,39 +298,9 @@ render_forward_kernel(ViewParams vp, bool no_color, const uint2* __restrict__ ra
 // launch geometry depends on a device-side count.
 __global__ void __launch_bounds__(1024)
 live_scan_kernel(int T, const uint32_t* __restrict__ max_contrib, uint32_t* __restrict__ live_offsets, ImageHeader* hdr) {
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        const uint32_t v = t < T ? (max_contrib[t] + BUCKET - 1) / BUCKET : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_tot[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += n;
-            }
-            warp_tot[lane] = wi - w;
-        }
-        __syncthreads();
-        const uint32_t out = carry + warp_tot[warp] + incl;
-        if (t < T) live_offsets[t] = out;
-        __syncthreads();
-        if (tid == 1023) carry = out;
-        __syncthreads();
-    }
-    if (tid == 0) { hdr->num_live_buckets = carry; hdr->bwd_ticket = 0; }
+    const uint32_t total = cta_scan_tiles(T, [&](int t) { return (max_contrib[t] + BUCKET - 1) / BUCKET; },
+                                          [&](int t, uint32_t v) { live_offsets[t] = v; });
+    if (threadIdx.x == 0) { hdr->num_live_buckets = total; hdr->bwd_ticket = 0; }
 }
 
 constexpr int BWD_WARPS = 4;              // warps per CTA; every warp owns one (live bucket, tile part) at a time
