@@ -401,7 +401,13 @@ def run_ours(args):
     mp.optimize(batch_host * 3)
     nat_ms, nat_windows, _ = timed_windows(mapper_window(batch_host), steps, world, dev, min_windows=3, min_total_ms=200.0)
     st = mp.stats()
+    capi.profile_enable(True)
+    mp.optimize(batch_host * steps)
+    nprof = capi.profile_read()
+    capi.profile_enable(False)
+    nat_stage = {kk: round(v[0] / (steps * (k if kk not in ("adam", "allreduce") else 1)), 4) for kk, v in nprof.items() if v[1]}
     native = {"ms_per_iter": round(nat_ms, 4), "views_per_iter": S, "loss": float(st.last_loss), "window_ms": nat_windows,
+              "stage_ms_per_iter": nat_stage,
               "what": "C++ mapper (csrc/mapper.cu, no torch, no Python in the loop): pinned keyframe image H2D on a copy stream "
                       "(double-buffered), fused activations, forward, fused L1/D-SSIM loss, backward to compact gradients%s, one masked "
                       "Adam launch that rebuilds dL/d(dc, sh) from dL/dcolour" % (

@@ -88,11 +88,11 @@ adam_packed_kernel(float* __restrict__ param, const float* __restrict__ grad, fl
 
 // ---- the mapper's Adam: compact gradients in, all six groups out (include/glic_b200.h "Native mapping host") -----------
 // One warp owns 32 consecutive Gaussians.  Phase 1 (lane = Gaussian): the union of the per-view visibility bytes decides
-// whether the Gaussian steps at all; the 11 geometric gradients (already summed over the rank's views and mean-reduced over
-// the ranks) and dc take their Adam update straight from registers; the sh-rest gradient -- never materialised by the
-// backward -- is rebuilt as  sum_views b_k(dir_view) * g_view  (b_k: sh_math.cuh, dir from the PRE-update xyz) into a
-// shared-memory slab.  Phase 2 (warp-cooperative, coalesced): the 32 x 3M sh-rest parameters and moments stream through
-// once, reading their gradient from the slab.  Element arithmetic = adam_element (adam_math.cuh), i.e. adamUpdateCUDA's.
+// whether the Gaussian steps at all; the dc and sh-rest gradients -- never materialised by the backward -- are rebuilt as
+// sum_views b_k(dir_view) * g_view (b_k: sh_math.cuh, dir from the PRE-update xyz) into a shared-memory slab.  Phase 2
+// (warp-cooperative): all six groups of the warp's visible rows stream through once with coalesced accesses, the geometric
+// gradients (already summed over the rank's views and mean-reduced over the ranks) read from the arena-shaped gradient block,
+// dc / sh-rest from the slab.
 struct ArenaLayout {
     size_t off[6];       // float offset of each group in the arena: rotation, xyz, log-scale, opacity, dc, sh-rest
     float lr[6];
@@ -113,25 +113,27 @@ adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float*
                     const float* __restrict__ g_geo /* arena-shaped: rotation | xyz | log-scale | opacity */, ArenaLayout L,
                     ArenaLayout Lg, ViewSlots vs, float grad_scale, float color_scale, float b1, float b2, float eps,
                     const unsigned int* __restrict__ skip_flag, unsigned int* __restrict__ visible_count) {
-    __shared__ float s_g[ADAM_WARPS][32 * SH_ROW_MAX];
-    __shared__ uint8_t s_vis[ADAM_WARPS][32];
+    __shared__ float s_g[ADAM_WARPS][32 * (SH_ROW_MAX + 3)];      // rebuilt gradients of the warp's 32 Gaussians: dc[32][3] | sh-rest[32][K]
+    __shared__ uint8_t s_row[ADAM_WARPS][32];                      // compacted list of the warp's visible rows
     if (skip_flag && *skip_flag) return;                          // binning overflow: the frame was empty, do not step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t wfirst = (blockIdx.x * ADAM_WARPS + warp) * 32u;
     if (wfirst >= P) return;
     const uint32_t i = wfirst + lane;
     const int K = 3 * M;
-    float* slab = s_g[warp];
+    float* s_dc = s_g[warp];
+    float* s_sh = s_g[warp] + 32 * 3;
     bool vis = false;
     if (i < P) {
         for (int v = 0; v < vs.n_slots; ++v) vis |= (vs.visible[(size_t)v * vs.stride + i] & 0x80u) != 0;
     }
-    s_vis[warp][lane] = vis ? 1 : 0;
     const unsigned any = __ballot_sync(0xffffffffu, vis);
-    if (visible_count && lane == 0 && any) atomicAdd(visible_count, (unsigned)__popc(any));
     if (!any) return;
+    const int nvis = __popc(any);
+    if (visible_count && lane == 0) atomicAdd(visible_count, (unsigned)nvis);
+    if (vis) s_row[warp][__popc(any & ((1u << lane) - 1u))] = (uint8_t)lane;
+    // ---- phase 1 (lane = Gaussian): dL/d(dc, sh-rest) from the per-view colour gradients, into shared memory ----
     if (vis) {
-        // ---- sh-rest gradient into the slab, dc gradient into registers (uses the pre-update position) ----
         const float px = params[L.off[1] + 3 * (size_t)i], py = params[L.off[1] + 3 * (size_t)i + 1], pz = params[L.off[1] + 3 * (size_t)i + 2];
         float gdc[3] = {0.f, 0.f, 0.f};
         const int nb = D > 0 ? sh_rest_count(D) : 0;
@@ -156,37 +158,54 @@ adam_compact_kernel(uint32_t P, int D, int M, float* __restrict__ params, float*
             }
         }
 #pragma unroll
-        for (int k = 0; k < SH_ROW_MAX; ++k) if (k < K) slab[lane * K + k] = acc[k] * color_scale;
-        // ---- geometric groups + dc: 14 scalars per Gaussian ----
-        auto step = [&](int grp, int kk, size_t j, float g) {
-            const size_t e = L.off[grp] + j;
-            float p = params[e], m = exp_avg[e], vv = exp_avg_sq[e];
-            adam_element(p, m, vv, g, L.lr[grp], b1, b2, eps);
-            params[e] = p; exp_avg[e] = m; exp_avg_sq[e] = vv;
-            (void)kk;
-        };
+        for (int c = 0; c < 3; ++c) s_dc[3 * lane + c] = gdc[c] * color_scale;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) step(0, 4, 4 * (size_t)i + c, g_geo[Lg.off[0] + 4 * (size_t)i + c] * grad_scale);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) step(1, 3, 3 * (size_t)i + c, g_geo[Lg.off[1] + 3 * (size_t)i + c] * grad_scale);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) step(2, 3, 3 * (size_t)i + c, g_geo[Lg.off[2] + 3 * (size_t)i + c] * grad_scale);
-        step(3, 1, (size_t)i, g_geo[Lg.off[3] + (size_t)i] * grad_scale);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) step(4, 3, 3 * (size_t)i + c, gdc[c] * color_scale);
+        for (int k = 0; k < SH_ROW_MAX; ++k) if (k < K) s_sh[lane * K + k] = acc[k] * color_scale;
     }
-    if (K == 0) return;
     __syncwarp();
-    // ---- sh-rest: 32 rows of K floats, contiguous in the arena; rows of invisible Gaussians are skipped ----
-    const int cnt = (int)min(32u, P - wfirst);
-    const size_t base = L.off[5] + (size_t)wfirst * K;
-    for (int e = lane; e < cnt * K; e += 32) {
-        const int row = e / K;
-        if (!s_vis[warp][row]) continue;
-        float p = params[base + e], m = exp_avg[base + e], vv = exp_avg_sq[base + e];
-        adam_element(p, m, vv, slab[e], L.lr[5], b1, b2, eps);
-        params[base + e] = p; exp_avg[base + e] = m; exp_avg_sq[base + e] = vv;
-    }
+    // ---- phase 2 (warp-cooperative, coalesced): every group's rows of the warp's visible Gaussians stream through once.  The
+    // 32 lanes walk the (visible row, column) pairs of a group 32 at a time; (row, column) advance incrementally (no division).
+    // Element arithmetic = adam_element (adam_math.cuh), i.e. adamUpdateCUDA's.
+    // Four 32-element steps are in flight per lane (12 independent loads issued before the first use; eight measured slower): the loop is latency-bound
+    // otherwise (one dependent global round trip per 32 elements).
+    auto run_group = [&](int grp, int kk, const float* grad_global, size_t goff, float gscale, const float* grad_smem) {
+        if (kk == 0) return;
+        constexpr int U = 4;
+        int r = 0, c = lane;
+        while (c >= kk) { c -= kk; ++r; }
+        const int step_r = 32 / kk, step_c = 32 % kk;
+        while (r < nvis) {
+            size_t e[U];
+            float g[U], p[U], m[U], vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ok[u] = r < nvis;
+                const int row = ok[u] ? s_row[warp][r] : 0;
+                e[u] = L.off[grp] + ((size_t)wfirst + row) * kk + c;
+                g[u] = 0.f;
+                if (ok[u]) {
+                    g[u] = grad_global ? grad_global[goff + ((size_t)wfirst + row) * kk + c] * gscale : grad_smem[row * kk + c];
+                    p[u] = params[e[u]]; m[u] = exp_avg[e[u]]; vv[u] = exp_avg_sq[e[u]];
+                }
+                r += step_r; c += step_c;
+                if (c >= kk) { c -= kk; ++r; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    adam_element(p[u], m[u], vv[u], g[u], L.lr[grp], b1, b2, eps);
+                    params[e[u]] = p[u]; exp_avg[e[u]] = m[u]; exp_avg_sq[e[u]] = vv[u];
+                }
+            }
+        }
+    };
+    run_group(0, 4, g_geo, Lg.off[0], grad_scale, nullptr);
+    run_group(1, 3, g_geo, Lg.off[1], grad_scale, nullptr);
+    run_group(2, 3, g_geo, Lg.off[2], grad_scale, nullptr);
+    run_group(3, 1, g_geo, Lg.off[3], grad_scale, nullptr);
+    run_group(4, 3, nullptr, 0, 0.f, s_dc);
+    run_group(5, K, nullptr, 0, 0.f, s_sh);
 }
 
 // rows [P, P+n) of the arena <- the new Gaussians; their sh-rest rows and Adam moments are zero (densificationPostfix)
