@@ -101,7 +101,7 @@ struct SsimMapOp : public torch::autograd::Function<SsimMapOp> {
 };
 
 inline Tensor photometric_loss(const Tensor& image, const Tensor& gt, double lambda_dssim) {
-    Tensor l1 = (image - gt).abs().mean();
+    Tensor l1 = torch::l1_loss(image, gt);                 // mean |image - gt| (loss_utils.h:30-33) as one fused ATen op
     Tensor ssim = SsimMapOp::apply(image.unsqueeze(0), gt.unsqueeze(0)).mean();
     return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - ssim);
 }

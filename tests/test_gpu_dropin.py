@@ -100,3 +100,36 @@ def test_dropin_distcuda2(ref_ext, dropin_ext):
     gen = torch.Generator(device="cuda").manual_seed(3)
     pts = torch.randn(30_000, 3, device="cuda", generator=gen) * 4.0
     torch.testing.assert_close(dropin_ext.distCUDA2(pts), ref_ext.distCUDA2(pts), rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("view,pp", POSES[1:3])
+def test_cpp_mapping_host_matches_reference(ref_ext, view, pp):
+    """csrc/torch_host.cpp (MappingHost: the loop body of optimize() written in C++ against the six boundary symbols; what
+    bench.py's e2e / mapping_iter legs time) against the reference build driven by the reference's own host code."""
+    from gaussian_lic_b200 import ops, synthetic as syn
+    P, W, H, deg, seed = 4096, 320, 208, 3, 11
+    g, cam = small_scene(P, W, H, seed, deg, view=view, pp=pp)
+    gt_host = torch.as_tensor(syn.make_gt_image(W, H)).pin_memory()
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    cam_host = torch.cat([t(cam["view"]), t(cam["proj"]), t(cam["campos"])]).pin_memory()
+    pa, pb = _params(g, P), _params(g, P)
+    host = ops.shim().MappingHost([pa[k].detach().clone() for k in ORDER], LRS, H, W, deg, cam["tanfovx"], cam["tanfovy"],
+                                  [float(x) for x in cam["lims"]], 0.2)
+    loss_a, radii_a = host.forward_backward(gt_host, cam_host)
+    ga = dict(zip(ORDER, [x.clone() for x in host.grads()]))
+    col_b, rad_b, loss_b, gb = _iteration(ref_ext, pb, cam, gt_host.cuda(), deg, P, H, W)
+    assert torch.equal(radii_a, rad_b)
+    assert abs(float(loss_a.item()) - loss_b) <= 2e-6
+    for k in ORDER:
+        grad_close(ga[k].cpu().numpy(), gb[k].cpu().numpy(), "C++ host d%s vs reference" % k, rtol=5e-4)
+    host.optimizer_step(radii_a > 0)
+    torch.cuda.synchronize()
+    vis = rad_b > 0
+    for k, lr, a in zip(ORDER, LRS, host.params()):
+        b = pb[k].detach()
+        assert torch.equal(a.detach()[~vis], b[~vis]), k
+        noise = gb[k].abs() <= 1e-4 * gb[k].abs().max()
+        d = (a.detach() - b).abs()
+        assert d[~noise].max().item() <= 0.05 * lr + 1e-7, (k, d[~noise].max().item(), lr)
+    e = host.e2e_step(gt_host, cam_host)                         # second iteration: runs, returns a finite loss, leaves no gradient behind
+    assert np.isfinite(e) and all(x is None for x in host.grads())
