@@ -12,6 +12,7 @@ Metric: Gaussians/s rasterised (forward + fused L1/D-SSIM loss + backward) at 19
               autograd, called from a C++ host (csrc/torch_host.cpp), with the per-iteration HOST inputs of the
               reference loop (gaussian.cpp:674-699): pinned ground-truth image + camera H2D every step,
               loss scalar D2H every step
+  e2e_native: the same step through ONE synchronous C-ABI call of the native mapper per step (pinned image H2D, loss D2H)
   mapping_iter / mapping_iter_native : BASELINE's second half, the body of optimize()'s loop, through the LibTorch
               symbols and through the native mapper
   sort_cfg5 : BASELINE configs[4] (50 M key/value pairs), appended to the N = 1 line of both arms
@@ -396,6 +397,24 @@ def run_ours(args):
         mp.close()
         return
 
+    # ---- e2e through the NATIVE host: one synchronous C-ABI call per step (glic_mapper_optimize on one view batch): pinned image
+    # H2D, the `value` step, loss D2H + host synchronisation every step; host wall clock over K calls, optimiser off ----------------
+    mp.set_optimizer(False)
+    for _ in range(3):
+        mp.optimize(batch_host)
+
+    def native_e2e_window():
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mp.optimize(batch_host)                          # returns after the stream is drained and the loss has been read
+        return (time.perf_counter() - t0) * 1e3
+
+    e2n_ms, e2n_windows, _ = timed_windows(native_e2e_window, steps, world, dev, min_windows=3, min_total_ms=200.0)
+    e2e_native = {"value": P * S / (e2n_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": round(e2n_ms, 4), "window_ms": e2n_windows,
+                  "h2d_bytes_per_step": int(gt_host.numel() * 4 * k), "d2h_bytes_per_step": 4 + 32,
+                  "api": "glic_mapper_optimize (C ABI, csrc/mapper.cu), one synchronous call per step: pinned keyframe image H2D, "
+                         "activations + forward + loss + backward%s, loss + binning counters D2H, host wall clock"
+                         % (" + NVLink exchange" if world > 1 else "")}
     # ---- native mapping iteration: pinned image H2D every iteration + the step above + the SH-rebuilding masked Adam --------
     mp.set_optimizer(True)
     mp.optimize(batch_host * 3)
@@ -504,7 +523,8 @@ def run_ours(args):
                       "host": "C++ mapper (csrc/mapper.cu), plain launches on one stream, no host synchronisation inside the window",
                       "l2": "per-step working set ~%.1f GB > 126 MB L2 (no explicit flush)" % (A1 * k / 1e9),
                       "binning_overflow_regrows": int(regrows)},
-           "clocks": clocks, "e2e": e2e, "mapping_iter": mapping, "mapping_iter_native": native, "gpu_launches": int(launches),
+           "clocks": clocks, "e2e": e2e, "e2e_native": e2e_native, "mapping_iter": mapping, "mapping_iter_native": native,
+           "gpu_launches": int(launches),
            "roofline": roofline, "cpu_baseline": cpu}
     if extra_sort is not None:
         out["sort_cfg5"] = extra_sort
