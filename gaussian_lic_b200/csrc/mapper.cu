@@ -115,7 +115,6 @@ struct glic_mapper {
     std::mt19937_64 rng;
     uint64_t view_counter = 0;
     glic_mapper_stats st{};
-    double vis_sum = 0; uint64_t vis_iters = 0;
     bool run_optimizer = true;            // GLIC_MAPPER_OPT_OPTIMIZER (benchmarks time the rasterization step alone with it off)
 };
 
@@ -240,6 +239,8 @@ __global__ void overflow_word_kernel(const GeomHeader* ghdr, float* word) { if (
 int iteration(glic_mapper* m, const int* views) {
     if (m->P == 0) return GLIC_OK;
     if (m->cfg.world > 1 && !m->connected) { set_error("mapper: world > 1 needs glic_mapper_connect before the first iteration"); return GLIC_ERR_INVALID_ARGUMENT; }
+    for (int sl = 0; sl < m->S; ++sl)
+        if (views[sl] < 0 || views[sl] >= (int)m->train.size()) { set_error("mapper: view index out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
     MAP_TRY(poll_ring(m, false));
     const int r = (int)(m->st.iterations % RING);
     if (m->ring_used[r]) { GLIC_CUDA_TRY(cudaEventSynchronize(m->ring_ev[r])); MAP_TRY(poll_ring(m, false)); }
@@ -257,9 +258,7 @@ int iteration(glic_mapper* m, const int* views) {
     glic_packed_offsets(m->Pcap, 0, goff);
     for (int j = 0; j < m->k; ++j) {
         const int slot = m->cfg.rank * m->k + j;
-        const int vi = views[slot];
-        if (vi < 0 || vi >= (int)m->train.size()) { set_error("mapper: view index out of range"); return GLIC_ERR_INVALID_ARGUMENT; }
-        const Keyframe& kf = m->train[vi];
+        const Keyframe& kf = m->train[views[slot]];
         const int buf = (int)(m->view_counter++ & 1);
         // keyframe image H2D on the copy stream (gaussian.cpp:678), overlapping the previous view's backward / Adam
         GLIC_CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->gt_free[buf], 0));
