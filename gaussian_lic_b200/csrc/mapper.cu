@@ -188,8 +188,8 @@ int set_capacity(glic_mapper* m, uint32_t cap) {
     return GLIC_OK;
 }
 
-int set_bin_capacity(glic_mapper* m, int64_t pairs) {
-    if (pairs <= m->bin_cap) return GLIC_OK;
+int set_bin_capacity(glic_mapper* m, int64_t pairs, bool exact = false) {
+    if (!exact && pairs <= m->bin_cap) return GLIC_OK;
     GLIC_CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (m->binning_ws) cudaFree(m->binning_ws);
     if (m->sample_ws) cudaFree(m->sample_ws);
@@ -610,6 +610,10 @@ int glic_mapper_set_option(glic_mapper* m, int option, int value) {
     if (!m) { set_error("mapper_set_option: null mapper"); return GLIC_ERR_INVALID_ARGUMENT; }
     switch (option) {
         case GLIC_MAPPER_OPT_OPTIMIZER: m->run_optimizer = value != 0; return GLIC_OK;
+        case GLIC_MAPPER_OPT_BINNING_PAIRS:            // start from a chosen (possibly too small) binning capacity: exercises the overflow path
+            if (value < 1) { set_error("mapper_set_option: binning capacity must be positive"); return GLIC_ERR_INVALID_ARGUMENT; }
+            MAP_TRY(poll_ring(m, true));
+            return set_bin_capacity(m, value, /*exact=*/true);
         default: set_error("mapper_set_option: unknown option"); return GLIC_ERR_INVALID_ARGUMENT;
     }
 }

@@ -116,6 +116,9 @@ class Mapper:
     def set_optimizer(self, on):
         capi.check(capi.lib.glic_mapper_set_option(self._h, 1, int(bool(on))), "mapper_set_option")
 
+    def set_binning_pairs(self, pairs):
+        capi.check(capi.lib.glic_mapper_set_option(self._h, 2, int(pairs)), "mapper_set_option")
+
     def synchronize(self):
         capi.check(capi.lib.glic_mapper_synchronize(self._h), "mapper_synchronize")
 

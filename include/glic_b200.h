@@ -394,7 +394,7 @@ GLIC_API int glic_mapper_synchronize(glic_mapper* m);
 /* options: GLIC_MAPPER_OPT_OPTIMIZER (default 1): 0 leaves the Adam launch out of the iteration, so that a benchmark can time
  * the rasterization step (activations, forward, loss, backward, exchange) on its own.  Keyframe images may be device pointers
  * (the copy uses cudaMemcpyDefault): that is how "inputs resident in HBM" is measured. */
-enum { GLIC_MAPPER_OPT_OPTIMIZER = 1 };
+enum { GLIC_MAPPER_OPT_OPTIMIZER = 1, GLIC_MAPPER_OPT_BINNING_PAIRS = 2 /* (tile, Gaussian) pairs the binning workspace holds; grows by itself on overflow */ };
 GLIC_API int glic_mapper_set_option(glic_mapper* m, int option, int value);
 /* Camera (camera.h:38-110) in closed form, as the mapper derives it from a keyframe pose: out41 = view[16] (column-major
  * Rt) | proj[16] (column-major P*Rt) | campos[3] | tan_fovx, tan_fovy | limx_neg, limx_pos, limy_neg, limy_pos. */
