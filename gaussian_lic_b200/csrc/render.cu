@@ -328,6 +328,9 @@ render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr
     __shared__ float4 s_sp[BWD_WARPS][BUCKET][3];            // the bucket's splat records, per warp
     __shared__ uint32_t s_gid[BWD_WARPS][BUCKET];
     __shared__ uint32_t s_rows[BWD_WARPS][BUCKET];           // row pairs each splat can reach (8-bit mask)
+    // dL/dpixel of the lane's pixel pairs, [pair][channel][lane] as packed (row pair 2p, row pair 2p+1) values: read-only inside a
+    // bucket, so it lives in shared memory instead of 24 registers (128 -> fewer registers = one more CTA per SM)
+    __shared__ float2 s_g[BWD_WARPS][BWD_ROWPAIRS / 2][3][32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_live = hdr->num_live_buckets;
@@ -380,7 +383,8 @@ render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr
         // inside this bucket (0 = never got here) and the restart state, kept in packed fp32x2 registers
         constexpr int NP = BWD_ROWPAIRS / 2;
         int rel[BWD_ROWPAIRS];
-        f2 Tr[NP], a0[NP], a1[NP], a2[NP], g0[NP], g1[NP], g2[NP], qy2[NP];
+        f2 Tr[NP], a0[NP], a1[NP], a2[NP];
+        const float qy0f = (float)qy0;
         int rel_max[BWD_ROWPAIRS];                            // warp-uniform: deepest pixel of each row pair
         int n_max = 0;
 #pragma unroll
@@ -407,8 +411,9 @@ render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr
             }
             Tr[p] = f2_pack(st[0][0], st[1][0]);
             a0[p] = f2_pack(st[0][1], st[1][1]); a1[p] = f2_pack(st[0][2], st[1][2]); a2[p] = f2_pack(st[0][3], st[1][3]);
-            g0[p] = f2_pack(st[0][4], st[1][4]); g1[p] = f2_pack(st[0][5], st[1][5]); g2[p] = f2_pack(st[0][6], st[1][6]);
-            qy2[p] = f2_pack((float)(qy0 + 4 * p), (float)(qy0 + 4 * p + 2));
+            s_g[warp][p][0][lane] = make_float2(st[0][4], st[1][4]);
+            s_g[warp][p][1][lane] = make_float2(st[0][5], st[1][5]);
+            s_g[warp][p][2][lane] = make_float2(st[0][6], st[1][6]);
         }
 
         // stage the bucket's splats (lane l <-> splat l) and the row pairs each one can reach
@@ -452,7 +457,7 @@ render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr
             for (int p = 0; p < NP; ++p) {
                 const unsigned two = (rows >> (2 * p)) & 3u;
                 if (!two) continue;                                       // warp-uniform
-                const f2 dy = f2_sub(f2_bcast(a.y), qy2[p]);
+                const f2 dy = f2_sub(f2_bcast(a.y), f2_pack(qy0f + (float)(4 * p), qy0f + (float)(4 * p + 2)));   // integers < 2^24: exact
                 // splat_power(dx, dy, cx, cy, cz) in the forward's operation order, both pixels at once
                 const f2 power = f2_sub(f2_mul(f2_fma(dx, cxdx, f2_mul(dy, f2_mul(dy, b.x))), -0.5f), f2_mul(dy, cydx));
                 float p0, p1;
@@ -473,12 +478,14 @@ render_backward_kernel(ViewParams vp, int T_tiles, ImageHeader* __restrict__ hdr
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(m0));
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(m1));
                 const f2 ainv = f2_pack(i0, i1);
-                a0[p] = f2_fma(dch, f2_bcast(b.z), a0[p]); c0s = f2_fma(dch, g0[p], c0s);
-                f2 dLa = f2_mul(f2_fma(ainv, a0[p], f2_mul(T, b.z)), g0[p]);
-                a1[p] = f2_fma(dch, f2_bcast(b.w), a1[p]); c1s = f2_fma(dch, g1[p], c1s);
-                dLa = f2_fma(f2_fma(ainv, a1[p], f2_mul(T, b.w)), g1[p], dLa);
-                a2[p] = f2_fma(dch, f2_bcast(c2), a2[p]); c2s = f2_fma(dch, g2[p], c2s);
-                dLa = f2_fma(f2_fma(ainv, a2[p], f2_mul(T, c2)), g2[p], dLa);
+                const float2 gr = s_g[warp][p][0][lane], gg = s_g[warp][p][1][lane], gb = s_g[warp][p][2][lane];
+                const f2 g0 = f2_pack(gr.x, gr.y), g1 = f2_pack(gg.x, gg.y), g2 = f2_pack(gb.x, gb.y);
+                a0[p] = f2_fma(dch, f2_bcast(b.z), a0[p]); c0s = f2_fma(dch, g0, c0s);
+                f2 dLa = f2_mul(f2_fma(ainv, a0[p], f2_mul(T, b.z)), g0);
+                a1[p] = f2_fma(dch, f2_bcast(b.w), a1[p]); c1s = f2_fma(dch, g1, c1s);
+                dLa = f2_fma(f2_fma(ainv, a1[p], f2_mul(T, b.w)), g1, dLa);
+                a2[p] = f2_fma(dch, f2_bcast(c2), a2[p]); c2s = f2_fma(dch, g2, c2s);
+                dLa = f2_fma(f2_fma(ainv, a2[p], f2_mul(T, c2)), g2, dLa);
                 Tr[p] = f2_mul(T, one_m);
                 // constant factors (opacity, 0.5*W, 0.5*H, -0.5) are applied once per splat below
                 const f2 w = f2_mul(G, dLa);                              // = dL_dG / opacity
@@ -561,7 +568,7 @@ int launch_render_backward(int P, const ViewParams& vp, int64_t max_buckets, con
     static const int rp = getenv("GLIC_BWD_RP") ? atoi(getenv("GLIC_BWD_RP")) : 8;
     using Kern = void (*)(ViewParams, int, ImageHeader*, const uint2*, const uint32_t*, const float4*, const uint32_t*,
                           const uint32_t*, const float4*, const uint32_t*, const float*, const float*, float*, float*, float*, float*);
-    const Kern kern = rp == 8 ? render_backward_kernel<8, 4> : render_backward_kernel<4, 6>;
+    const Kern kern = rp == 8 ? render_backward_kernel<8, 5> : render_backward_kernel<4, 6>;
     static int blocks_per_device[64] = {};
     int dev = 0;
     GLIC_CUDA_TRY(cudaGetDevice(&dev));
