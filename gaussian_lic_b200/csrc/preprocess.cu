@@ -108,6 +108,7 @@ struct WalkSmem {
     int x0[PRE_THREADS], y0[PRE_THREADS], rw[PRE_THREADS], n[PRE_THREADS];
     uint32_t off[PRE_THREADS], idx[PRE_THREADS];
     uint32_t base[PRE_THREADS];               // first entry of the rect's row spans in the span arena (NO_SPANS: none)
+    uint32_t small_mask[PRE_THREADS];         // accept bits of the small rects, gathered from the flat candidate test
     uint32_t warp_big[PRE_THREADS / 32];
     uint32_t n_big, n_rows;
 };
@@ -196,22 +197,59 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
         }
         w.base[slot] = mask_or_base;
     }
-    // -- small rects: own lane, row-major, every tile tested
+    // -- small rects (<= 32 tiles).  EMIT: own lane expands its stored mask.  COUNT: the warp's (Gaussian, tile) candidates are
+    // tested FLAT -- lane l takes candidates l, l + 32, ... of the warp's concatenated rects and finds its Gaussian with a 5-step
+    // search over the inclusive counts (parameters fetched by shuffle) -- so a warp needs ceil(sum n / 32) rounds instead of
+    // max n rounds with most lanes idle (median rect 4 tiles, maximum 32).  The accept bits return to the owning lane through a
+    // 32-word per-warp mask array.
     uint32_t count = 0;
-    if (n > 0 && !big) {
-        int tx = x0, ty = y0;
-        const int x1 = x0 + rw;
-        uint32_t mask = EMIT ? mask_or_base : 0u;
-        for (int t = 0; t < n; ++t) {
-            const bool in = EMIT ? ((mask >> t) & 1u) != 0 : tile_max_power(cox, coy, coz, mx, my, tx, ty) <= thr;
-            if (in) {
-                if (EMIT) { const uint32_t key = (uint32_t)(ty * grid_x + tx); keys[off + count] = key; vals[off + count] = idx; count_key(key); }
-                else mask |= 1u << t;
-                ++count;
+    if (EMIT) {
+        if (n > 0 && !big) {
+            int tx = x0, ty = y0;
+            const int x1 = x0 + rw;
+            const uint32_t mask = mask_or_base;
+            for (int t = 0; t < n; ++t) {
+                if ((mask >> t) & 1u) {
+                    const uint32_t key = (uint32_t)(ty * grid_x + tx);
+                    keys[off + count] = key; vals[off + count] = idx; count_key(key);
+                    ++count;
+                }
+                if (++tx == x1) { tx = x0; ++ty; }
             }
-            if (++tx == x1) { tx = x0; ++ty; }
         }
-        if (!EMIT) mask_or_base = mask;
+    } else {
+        const uint32_t ns = (n > 0 && !big) ? (uint32_t)n : 0u;
+        uint32_t fin = ns;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, fin, o);
+            if (lane >= o) fin += t;
+        }
+        const uint32_t tot = __shfl_sync(FULL, fin, 31);
+        w.small_mask[tid] = 0u;
+        __syncwarp();
+        const uint32_t recip = (65536u + (uint32_t)rw - 1u) / (uint32_t)rw;      // j / rw == (j * recip) >> 16 for j < 32, rw <= 32
+        for (uint32_t e = lane; e < ((tot + 31u) & ~31u); e += 32) {
+            int r = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const uint32_t probe = __shfl_sync(FULL, fin, r + st - 1);
+                if (probe <= e) r += st;
+            }
+            const uint32_t r_fin = __shfl_sync(FULL, fin, r), r_n = __shfl_sync(FULL, ns, r);
+            const float r_mx = __shfl_sync(FULL, mx, r), r_my = __shfl_sync(FULL, my, r), r_thr = __shfl_sync(FULL, thr, r);
+            const float r_cox = __shfl_sync(FULL, cox, r), r_coy = __shfl_sync(FULL, coy, r), r_coz = __shfl_sync(FULL, coz, r);
+            const int r_x0 = __shfl_sync(FULL, x0, r), r_y0 = __shfl_sync(FULL, y0, r), r_rw = __shfl_sync(FULL, rw, r);
+            const uint32_t r_rc = __shfl_sync(FULL, recip, r);
+            if (e < tot) {
+                const uint32_t j = e - (r_fin - r_n);                               // candidate index inside the rect, row-major
+                const uint32_t q = (j * r_rc) >> 16;
+                const int tx = r_x0 + (int)(j - q * (uint32_t)r_rw), ty = r_y0 + (int)q;
+                if (tile_max_power(r_cox, r_coy, r_coz, r_mx, r_my, tx, ty) <= r_thr) atomicOr(&w.small_mask[(tid & ~31) + r], 1u << j);
+            }
+        }
+        __syncwarp();
+        if (ns) { mask_or_base = w.small_mask[tid]; count = (uint32_t)__popc(mask_or_base); }
     }
     __syncthreads();
     if (total_big == 0) return count;
