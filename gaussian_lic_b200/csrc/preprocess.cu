@@ -204,19 +204,37 @@ GLIC_DI uint32_t block_tile_walk(WalkSmem& w, int n, float mx, float my, float c
     // 32-word per-warp mask array.
     uint32_t count = 0;
     if (EMIT) {
-        if (n > 0 && !big) {
-            int tx = x0, ty = y0;
-            const int x1 = x0 + rw;
-            const uint32_t mask = mask_or_base;
-            for (int t = 0; t < n; ++t) {
-                if ((mask >> t) & 1u) {
-                    const uint32_t key = (uint32_t)(ty * grid_x + tx);
-                    keys[off + count] = key; vals[off + count] = idx; count_key(key);
-                    ++count;
-                }
-                if (++tx == x1) { tx = x0; ++ty; }
+        // accepted tiles of the warp's small rects, written flat: lane l takes pairs l, l + 32, ... and finds its Gaussian by the
+        // same 5-step search; the k-th accepted tile of a rect is the k-th set bit of its mask
+        const uint32_t mask = (n > 0 && !big) ? mask_or_base : 0u;
+        const uint32_t cnt_s = (uint32_t)__popc(mask);
+        uint32_t fin = cnt_s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, fin, o);
+            if (lane >= o) fin += t;
+        }
+        const uint32_t tot = __shfl_sync(FULL, fin, 31);
+        const uint32_t recip = (65536u + (uint32_t)rw - 1u) / (uint32_t)rw;
+        for (uint32_t e = lane; e < ((tot + 31u) & ~31u); e += 32) {
+            int r = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const uint32_t probe = __shfl_sync(FULL, fin, r + st - 1);
+                if (probe <= e) r += st;
+            }
+            const uint32_t r_fin = __shfl_sync(FULL, fin, r), r_cnt = __shfl_sync(FULL, cnt_s, r), r_mask = __shfl_sync(FULL, mask, r);
+            const uint32_t r_off = __shfl_sync(FULL, off, r), r_idx = __shfl_sync(FULL, idx, r), r_rc = __shfl_sync(FULL, recip, r);
+            const int r_x0 = __shfl_sync(FULL, x0, r), r_y0 = __shfl_sync(FULL, y0, r), r_rw = __shfl_sync(FULL, rw, r);
+            if (e < tot) {
+                const uint32_t kth = e - (r_fin - r_cnt);                           // which accepted tile of the rect
+                const uint32_t j = __fns(r_mask, 0, (int)kth + 1);                  // its candidate index (row-major)
+                const uint32_t q = (j * r_rc) >> 16;
+                const uint32_t key = (uint32_t)((r_y0 + (int)q) * grid_x + r_x0 + (int)(j - q * (uint32_t)r_rw));
+                keys[r_off + kth] = key; vals[r_off + kth] = r_idx; count_key(key);
             }
         }
+        count = cnt_s;
     } else {
         const uint32_t ns = (n > 0 && !big) ? (uint32_t)n : 0u;
         uint32_t fin = ns;
