@@ -300,3 +300,16 @@ def test_binning_overflow_skips_the_step_and_recovers():
     ref6 = dict(rotation=ref["rots"], xyz=ref["means"], scaling=ref["log_scales"], opacity=ref["opacity_logits"], f_dc=ref["dc"], f_rest=ref["sh"])
     _compare(moved, ref6, 3, "after an overflowed + skipped step vs a clean run")
     m.close(); m2.close()
+
+
+def test_plain_c_host_runs_the_loop(tmp_path):
+    """examples/mapper_loop.c compiled as C99 and run: per keyframe extend + optimize, evaluation, map export; the program's own
+    exit code checks that the loss went down and the arena grew past its deliberately small initial capacity."""
+    import subprocess
+    from test_mapper_host import _build_c_host
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([str(exe), "4", "20000"], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    lines = r.stdout.splitlines()
+    assert sum(l.startswith("keyframe ") for l in lines) == 4 and lines[-1].startswith("done:")

@@ -31,3 +31,28 @@ def test_mapper_refuses_to_run_without_a_gpu():
     bad = capi.MapperConfig()                                                # a zeroed configuration is rejected before any CUDA call
     h = C.c_void_p()
     assert capi.lib.glic_mapper_create(C.byref(bad), C.byref(h)) == -1 and not h.value
+
+
+def _build_c_host(tmp_path):
+    import os
+    import subprocess
+    from gaussian_lic_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "mapper_loop"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cmd = ["/usr/bin/gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+           os.path.join(root, "examples", "mapper_loop.c"), "-o", str(exe), "-L", libdir, "-l:libglic_b200.so", "-Wl,-rpath," + libdir, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_host_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/mapper_loop.c: the whole mapping loop from C99 against include/glic_b200.h -- no torch, no Python."""
+    import subprocess
+    torch = pytest.importorskip("torch")
+    exe = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is tests/test_gpu_mapper.py::test_plain_c_host_runs_the_loop")
+    r = subprocess.run([str(exe), "2", "2000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
